@@ -1,0 +1,544 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[m, n] = sum_k A[m, k] * B[n, k]     fp16 operands, fp32 accumulation in TMEM.
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0   : TMA producer  (A tile 128 x 64 and B tile BN x 64 per stage, 128B-swizzled)
+//   warp 1   : MMA issuer    (one elected lane issues tcgen05.mma 128 x BN x 16, 4 per stage)
+//   warps 2-5: epilogue      (tcgen05.ld of the accumulator, fused bias / row-bias / GEGLU /
+//                             residual, fp16 stores) — overlaps the next tile's main loop through
+//                             two TMEM accumulator buffers.
+// Convolution mode walks K as (tap, channel block): for every tap the A tile is one 4-D TMA box
+// [bn images, bh rows, bw cols, 64 ch] shifted by (kh-1, kw-1); out-of-bounds pixels are
+// zero-filled by TMA, which is exactly the conv's zero padding.  The skip concat is a second
+// A source selected per channel block.
+//
+// Algorithmic bytes per launch: 2*(M*K + N*K + M*N [+ M*N residual]) ; FLOPs 2*M*N*K.
+#include "host_common.h"
+#include "ptx.cuh"
+#include "../../include/mdk.h"
+
+namespace mdk {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  CUtensorMap tmA0, tmA1, tmB;
+  int M, N;
+  int kb0, kb1;  // 64-wide K blocks (per tap) from source 0 / 1
+  int k0;        // K extent of source 0 (B column offset of source 1 inside a tap)
+  int ktap;      // k0 + k1: B columns per tap
+  int taps;
+  int H, W, nimg, bw, bh, bn, tiles_w, tiles_h;
+  int m_tiles, n_tiles;
+  const float* bias;
+  const float* row_bias;
+  int row_div, row_mod;
+  const __half* residual;
+  long long ldr;
+  int geglu;
+  int seg_cols;
+  __half* out[3];
+  long long ldo[3];
+  int out_trans[3];
+  int trans_rows;
+  long long trans_ld;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static constexpr int TMEM_COLS = (2 * BN <= 32)    ? 32
+                                   : (2 * BN <= 64)  ? 64
+                                   : (2 * BN <= 128) ? 128
+                                   : (2 * BN <= 256) ? 256
+                                                     : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;           // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmB);
+    if (p.kb1 > 0) tma_prefetch_desc(&p.tmA1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int kblocks_per_tap = p.kb0 + p.kb1;
+  const int num_kb = p.taps * kblocks_per_tap;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int n0 = n_tile * BN;
+        int m0 = m_tile * BM;
+        int img0 = 0, h0 = 0, w0 = 0;
+        if (p.taps > 1) {
+          const int tw = m_tile % p.tiles_w;
+          const int th = (m_tile / p.tiles_w) % p.tiles_h;
+          const int tn = m_tile / (p.tiles_w * p.tiles_h);
+          w0 = tw * p.bw;
+          h0 = th * p.bh;
+          img0 = tn * p.bn;
+        }
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dh = (p.taps > 1) ? (tap / 3 - 1) : 0;
+          const int dw = (p.taps > 1) ? (tap % 3 - 1) : 0;
+          for (int kb = 0; kb < kblocks_per_tap; ++kb) {
+            const bool src1 = kb >= p.kb0;
+            const int kk = (src1 ? (kb - p.kb0) : kb) * BK;
+            const int bcol = tap * p.ktap + (src1 ? p.k0 + kk : kk);
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            const CUtensorMap* ta = src1 ? &p.tmA1 : &p.tmA0;
+            if (p.taps > 1) {
+              tma_load_4d(smem_a + stage * A_TILE_BYTES, ta, &full_bar[stage], kk, w0 + dw, h0 + dh,
+                          img0);
+            } else {
+              tma_load_2d(smem_a + stage * A_TILE_BYTES, ta, &full_bar[stage], kk, m0);
+            }
+            tma_load_2d(smem_b + stage * Cfg::B_TILE_BYTES, &p.tmB, &full_bar[stage], bcol, n0);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t acc_phase[2] = {0, 0};
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase[acc] ^ 1u);
+      acc_phase[acc] ^= 1u;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = make_sdesc_sw128(smem_u32(smem_a + stage * A_TILE_BYTES));
+          const uint64_t bdesc = make_sdesc_sw128(smem_u32(smem_b + stage * Cfg::B_TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
+            tc_mma_f16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k),
+                          bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);                       // frees the smem stage when MMAs retire
+          if (kb == num_kb - 1) tc_commit(&tfull_bar[acc]);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue warps =======================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;
+    uint32_t acc_phase[2] = {0, 0};
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int n0 = n_tile * BN;
+      long long m;  // global output row of this thread, -1 if out of range
+      if (p.taps > 1) {
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int wi = row_in_tile % p.bw;
+        const int hi = (row_in_tile / p.bw) % p.bh;
+        const int ni = row_in_tile / (p.bw * p.bh);
+        const int img = tn * p.bn + ni;
+        m = (img < p.nimg)
+                ? (static_cast<long long>(img) * p.H + (th * p.bh + hi)) * p.W + (tw * p.bw + wi)
+                : -1;
+      } else {
+        m = static_cast<long long>(m_tile) * BM + row_in_tile;
+        if (m >= p.M) m = -1;
+      }
+      const float* rb = nullptr;
+      if (p.row_bias != nullptr && m >= 0)
+        rb = p.row_bias + static_cast<long long>((m / p.row_div) % p.row_mod) * p.N;
+
+      mbar_wait(&tfull_bar[acc], acc_phase[acc]);
+      acc_phase[acc] ^= 1u;
+      tc_fence_after();
+      const uint32_t t_acc =
+          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
+
+      if (p.geglu) {
+        // tile columns [0, BN/2) are values, [BN/2, BN) the matching gates
+        constexpr int HALF = BN / 2;
+        const int ocol0 = n_tile * HALF;
+        for (int c = 0; c < HALF; c += 32) {
+          if (n0 + c >= p.N) break;
+          uint32_t vh[32], vg[32];
+          tmem_ld_x32(t_acc + c, vh);
+          tmem_ld_x32(t_acc + HALF + c, vg);
+          tmem_wait_ld();
+          if (m >= 0) {
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float hval = __uint_as_float(vh[j]);
+              float gval = __uint_as_float(vg[j]);
+              if (p.bias) {
+                hval += __ldg(p.bias + n0 + c + j);
+                gval += __ldg(p.bias + n0 + HALF + c + j);
+              }
+              o[j] = hval * gelu_erf(gval);
+            }
+            __half* dst = p.out[0] + m * p.ldo[0] + ocol0 + c;
+            if (p.residual) {
+              const __half* rsrc = p.residual + m * p.ldr + ocol0 + c;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 rv = *reinterpret_cast<const uint4*>(rsrc + q * 8);
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __half22float2(rh[e]);
+                  o[q * 8 + 2 * e] += f.x;
+                  o[q * 8 + 2 * e + 1] += f.y;
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 pk;
+              pk.x = pack_half2(o[q * 8 + 0], o[q * 8 + 1]);
+              pk.y = pack_half2(o[q * 8 + 2], o[q * 8 + 3]);
+              pk.z = pack_half2(o[q * 8 + 4], o[q * 8 + 5]);
+              pk.w = pack_half2(o[q * 8 + 6], o[q * 8 + 7]);
+              *reinterpret_cast<uint4*>(dst + q * 8) = pk;
+            }
+          }
+        }
+      } else {
+        const int seg = (p.seg_cols > 0) ? (n0 / p.seg_cols) : 0;
+        const int seg_col0 = (p.seg_cols > 0) ? (n0 - seg * p.seg_cols) : n0;
+        __half* obase = p.out[seg];
+        const long long ldo = p.ldo[seg];
+        const bool trans = p.out_trans[seg] != 0;
+        for (int c = 0; c < BN; c += 32) {
+          if (n0 + c >= p.N) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_x32(t_acc + c, v);
+          tmem_wait_ld();
+          if (m >= 0) {
+            float o[32];
+            const int nvalid = min(32, p.N - (n0 + c));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(v[j]);
+              if (j < nvalid) {
+                if (p.bias) x += __ldg(p.bias + n0 + c + j);
+                if (rb) x += __ldg(rb + n0 + c + j);
+              }
+              o[j] = x;
+            }
+            if (p.residual) {
+              const __half* rsrc = p.residual + m * p.ldr + n0 + c;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (q * 8 < nvalid) {
+                  uint4 rv = *reinterpret_cast<const uint4*>(rsrc + q * 8);
+                  const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float2 f = __half22float2(rh[e]);
+                    o[q * 8 + 2 * e] += f.x;
+                    o[q * 8 + 2 * e + 1] += f.y;
+                  }
+                }
+              }
+            }
+            if (!trans) {
+              __half* dst = obase + m * ldo + seg_col0 + c;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (q * 8 < nvalid) {
+                  uint4 pk;
+                  pk.x = pack_half2(o[q * 8 + 0], o[q * 8 + 1]);
+                  pk.y = pack_half2(o[q * 8 + 2], o[q * 8 + 3]);
+                  pk.z = pack_half2(o[q * 8 + 4], o[q * 8 + 5]);
+                  pk.w = pack_half2(o[q * 8 + 6], o[q * 8 + 7]);
+                  *reinterpret_cast<uint4*>(dst + q * 8) = pk;
+                }
+              }
+            } else {
+              // per-image transposed store: lanes hold consecutive rows -> 64-byte runs per column
+              const long long img = m / p.trans_rows;
+              const long long l = m % p.trans_rows;
+              __half* dst = obase + (img * p.seg_cols + seg_col0 + c) * p.trans_ld + l;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < nvalid) dst[static_cast<long long>(j) * p.trans_ld] = __float2half_rn(o[j]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int pick_bn(int n, int seg_cols, int nseg) {
+  const int cands[] = {256, 192, 160, 128, 64, 32};
+  int best = 0;
+  long long best_pad = 0;
+  for (int bn : cands) {
+    if (nseg > 1 && (seg_cols % bn) != 0) continue;
+    long long pad = static_cast<long long>((n + bn - 1) / bn) * bn;
+    if (best == 0 || pad < best_pad) {
+      best = bn;
+      best_pad = pad;
+    }
+  }
+  return best;
+}
+
+// largest power of two <= cap that divides x
+static int pow2_div(int x, int cap) {
+  int r = 1;
+  while (r * 2 <= cap && (x % (r * 2)) == 0) r *= 2;
+  return r;
+}
+
+template <int BN>
+static int launch_gemm(const mdk_ctx* ctx, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;  // per kernel instantiation; benign race (idempotent)
+  if (!attr_set) {
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  count_launch();
+  MDK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mdk
+
+extern "C" int mdk_gemm_geglu_block(void) { return 256; }
+
+extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_) {
+  using namespace mdk;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MDK_REQUIRE(ctx && a, "mdk_gemm_f16: null ctx/args");
+  MDK_REQUIRE(a->a0 && a->b && a->out[0], "mdk_gemm_f16: null operand");
+  MDK_REQUIRE(a->m > 0 && a->n > 0 && a->k0 > 0, "mdk_gemm_f16: empty problem m=%d n=%d k0=%d",
+              a->m, a->n, a->k0);
+  MDK_REQUIRE(a->k0 % 8 == 0 && a->k1 % 8 == 0 && a->n % 8 == 0,
+              "mdk_gemm_f16: k0=%d k1=%d n=%d must be multiples of 8", a->k0, a->k1, a->n);
+  MDK_REQUIRE(a->ldb % 8 == 0, "mdk_gemm_f16: ldb=%lld must be a multiple of 8", (long long)a->ldb);
+  MDK_REQUIRE(a->conv_taps == 1 || a->conv_taps == 9, "mdk_gemm_f16: conv_taps must be 1 or 9");
+  MDK_REQUIRE((reinterpret_cast<uintptr_t>(a->a0) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->b) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->a1) & 15) == 0,
+              "mdk_gemm_f16: operands must be 16-byte aligned");
+  const int ktap = a->k0 + a->k1;
+  const long long K = static_cast<long long>(a->conv_taps) * ktap;
+  MDK_REQUIRE(a->ldb >= K, "mdk_gemm_f16: ldb=%lld < K=%lld", (long long)a->ldb, K);
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->m;
+  p.N = a->n;
+  p.k0 = a->k0;
+  p.ktap = ktap;
+  p.kb0 = (a->k0 + BK - 1) / BK;
+  p.kb1 = (a->k1 + BK - 1) / BK;
+  p.taps = a->conv_taps;
+  p.bias = a->bias;
+  p.row_bias = a->row_bias;
+  p.row_div = a->row_div > 0 ? a->row_div : 1;
+  p.row_mod = a->row_mod > 0 ? a->row_mod : 1;
+  p.residual = static_cast<const __half*>(a->residual);
+  p.ldr = a->ldr;
+  p.geglu = a->geglu;
+  p.seg_cols = a->seg_cols;
+  p.trans_rows = a->trans_rows > 0 ? a->trans_rows : 1;
+  p.trans_ld = a->trans_ld;
+  int nseg = 1;
+  const int ncols_out = a->geglu ? a->n / 2 : a->n;
+  if (a->seg_cols > 0) {
+    MDK_REQUIRE(!a->geglu, "mdk_gemm_f16: seg_cols with geglu is not supported");
+    MDK_REQUIRE(ncols_out % a->seg_cols == 0 && ncols_out / a->seg_cols <= 3,
+                "mdk_gemm_f16: n=%d is not 1..3 segments of %d", ncols_out, a->seg_cols);
+    nseg = ncols_out / a->seg_cols;
+  }
+  for (int s = 0; s < 3; ++s) {
+    p.out[s] = static_cast<__half*>(a->out[s]);
+    p.ldo[s] = a->ldo[s];
+    p.out_trans[s] = a->out_trans[s];
+    if (s < nseg) {
+      MDK_REQUIRE(a->out[s] != nullptr, "mdk_gemm_f16: out[%d] is NULL", s);
+      if (a->out_trans[s])
+        MDK_REQUIRE(a->seg_cols > 0 && a->trans_ld > 0,
+                    "mdk_gemm_f16: transposed output needs seg_cols and trans_ld");
+      else
+        MDK_REQUIRE(a->ldo[s] % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out[s]) & 15) == 0,
+                    "mdk_gemm_f16: out[%d] must be 16-byte aligned with ldo %% 8 == 0", s);
+    }
+  }
+  if (a->residual)
+    MDK_REQUIRE(a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0,
+                "mdk_gemm_f16: residual must be 16-byte aligned with ldr %% 8 == 0");
+
+  int bn;
+  if (a->geglu) {
+    bn = 256;
+    MDK_REQUIRE(a->n % 256 == 0, "mdk_gemm_f16: geglu needs n %% 256 == 0 (n=%d)", a->n);
+  } else {
+    bn = pick_bn(a->n, a->seg_cols, nseg);
+    MDK_REQUIRE(bn > 0, "mdk_gemm_f16: no tile width divides seg_cols=%d", a->seg_cols);
+  }
+  p.n_tiles = (a->n + bn - 1) / bn;
+
+  // ---- tensor maps ----
+  if (a->conv_taps == 1) {
+    MDK_REQUIRE(a->lda0 % 8 == 0 && a->lda0 >= a->k0, "mdk_gemm_f16: bad lda0=%lld",
+                (long long)a->lda0);
+    p.m_tiles = (a->m + BM - 1) / BM;
+    uint64_t dims[2] = {static_cast<uint64_t>(a->k0), static_cast<uint64_t>(a->m)};
+    uint64_t str[2] = {0, static_cast<uint64_t>(a->lda0) * 2};
+    uint32_t box[2] = {BK, BM};
+    if (encode_tmap_f16(&p.tmA0, a->a0, 2, dims, str, box)) return -1;
+    if (a->k1 > 0) {
+      MDK_REQUIRE(a->a1 && a->lda1 % 8 == 0 && a->lda1 >= a->k1, "mdk_gemm_f16: bad a1/lda1");
+      uint64_t dims1[2] = {static_cast<uint64_t>(a->k1), static_cast<uint64_t>(a->m)};
+      uint64_t str1[2] = {0, static_cast<uint64_t>(a->lda1) * 2};
+      if (encode_tmap_f16(&p.tmA1, a->a1, 2, dims1, str1, box)) return -1;
+    }
+  } else {
+    MDK_REQUIRE(a->nimg > 0 && a->h > 0 && a->w > 0 &&
+                    static_cast<long long>(a->nimg) * a->h * a->w == a->m,
+                "mdk_gemm_f16: conv needs m == nimg*h*w");
+    p.H = a->h;
+    p.W = a->w;
+    p.nimg = a->nimg;
+    p.bw = pow2_div(a->w, 16);
+    p.bh = pow2_div(a->h, BM / p.bw);
+    p.bn = BM / (p.bw * p.bh);
+    p.tiles_w = a->w / p.bw;
+    p.tiles_h = a->h / p.bh;
+    const int tiles_n = (a->nimg + p.bn - 1) / p.bn;
+    p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+    uint32_t box[4] = {BK, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh),
+                       static_cast<uint32_t>(p.bn)};
+    {
+      const uint64_t c = static_cast<uint64_t>(a->k0);
+      uint64_t dims[4] = {c, static_cast<uint64_t>(a->w), static_cast<uint64_t>(a->h),
+                          static_cast<uint64_t>(a->nimg)};
+      uint64_t str[4] = {0, c * 2, c * 2 * a->w, c * 2 * a->w * a->h};
+      if (encode_tmap_f16(&p.tmA0, a->a0, 4, dims, str, box)) return -1;
+    }
+    if (a->k1 > 0) {
+      MDK_REQUIRE(a->a1 != nullptr, "mdk_gemm_f16: a1 is NULL with k1 > 0");
+      const uint64_t c = static_cast<uint64_t>(a->k1);
+      uint64_t dims[4] = {c, static_cast<uint64_t>(a->w), static_cast<uint64_t>(a->h),
+                          static_cast<uint64_t>(a->nimg)};
+      uint64_t str[4] = {0, c * 2, c * 2 * a->w, c * 2 * a->w * a->h};
+      if (encode_tmap_f16(&p.tmA1, a->a1, 4, dims, str, box)) return -1;
+    }
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(a->n)};
+    uint64_t str[2] = {0, static_cast<uint64_t>(a->ldb) * 2};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
+    if (encode_tmap_f16(&p.tmB, a->b, 2, dims, str, box)) return -1;
+  }
+
+  switch (bn) {
+    case 256: return launch_gemm<256>(ctx, p, stream);
+    case 192: return launch_gemm<192>(ctx, p, stream);
+    case 160: return launch_gemm<160>(ctx, p, stream);
+    case 128: return launch_gemm<128>(ctx, p, stream);
+    case 64: return launch_gemm<64>(ctx, p, stream);
+    case 32: return launch_gemm<32>(ctx, p, stream);
+  }
+  return set_error("mdk_gemm_f16: internal: bad tile width %d", bn);
+}

@@ -1,0 +1,305 @@
+// GroupNorm (per image, NHWC, one or two channel-concatenated sources, optional SiLU) and
+// LayerNorm (+ optional reference-bank add) — HBM-bound kernels, fp32 math, 16-byte vector IO.
+//
+// Algorithmic bytes: GroupNorm reads the input twice (stats pass + apply pass) and writes once:
+// 3 * 2 * nimg*hw*C bytes; LayerNorm reads once, writes once (twice with the bank output).
+#include "host_common.h"
+#include "ptx.cuh"
+#include "../../include/mdk.h"
+
+namespace mdk {
+
+struct GnParams {
+  const __half* x0;
+  const __half* x1;
+  int c0, c1, C;
+  int nimg, hw, groups, cpg;
+  float eps;
+  const __half* gamma;
+  const __half* beta;
+  int silu;
+  __half* out;
+  double* ws;  // [nimg, groups, 2] sum, sumsq
+  int pix_per_cta;
+};
+
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 f = __half22float2(h[e]);
+    v[2 * e] = f.x;
+    v[2 * e + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+  uint4 pk;
+  pk.x = pack_half2(v[0], v[1]);
+  pk.y = pack_half2(v[2], v[3]);
+  pk.z = pack_half2(v[4], v[5]);
+  pk.w = pack_half2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = pk;
+}
+
+// blockDim = (vx, vy): thread x owns channel vector cv = threadIdx.x (8 channels), thread y strides
+// over the pixels of this CTA's slab.
+__global__ void gn_stats_kernel(const GnParams p) {
+  extern __shared__ float s_acc[];  // [groups*2]
+  const int img = blockIdx.y;
+  const int cv = threadIdx.x;
+  const int V = p.C >> 3;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < p.groups * 2; i += blockDim.x * blockDim.y) s_acc[i] = 0.f;
+  __syncthreads();
+  if (cv < V) {
+    const int ch = cv * 8;
+    const bool from1 = ch >= p.c0;
+    const __half* src = from1 ? p.x1 : p.x0;
+    const int cs = from1 ? p.c1 : p.c0;
+    const int coff = from1 ? ch - p.c0 : ch;
+    const int pbeg = blockIdx.x * p.pix_per_cta;
+    const int pend = min(p.hw, pbeg + p.pix_per_cta);
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+    for (int px = pbeg + threadIdx.y; px < pend; px += blockDim.y) {
+      float v[8];
+      load8(src + (static_cast<long long>(img) * p.hw + px) * cs + coff, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s[e] += v[e];
+        q[e] += v[e] * v[e];
+      }
+    }
+    // combine the (at most a few) groups this vector touches
+    int g_prev = ch / p.cpg;
+    float gs = 0.f, gq = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int g = (ch + e) / p.cpg;
+      if (g != g_prev) {
+        atomicAdd(&s_acc[g_prev * 2], gs);
+        atomicAdd(&s_acc[g_prev * 2 + 1], gq);
+        gs = gq = 0.f;
+        g_prev = g;
+      }
+      gs += s[e];
+      gq += q[e];
+    }
+    atomicAdd(&s_acc[g_prev * 2], gs);
+    atomicAdd(&s_acc[g_prev * 2 + 1], gq);
+  }
+  __syncthreads();
+  for (int i = tid; i < p.groups * 2; i += blockDim.x * blockDim.y)
+    atomicAdd(&p.ws[static_cast<long long>(img) * p.groups * 2 + i], static_cast<double>(s_acc[i]));
+}
+
+__global__ void gn_apply_kernel(const GnParams p) {
+  const int img = blockIdx.y;
+  const int cv = threadIdx.x;
+  const int V = p.C >> 3;
+  if (cv >= V) return;
+  const int ch = cv * 8;
+  const bool from1 = ch >= p.c0;
+  const __half* src = from1 ? p.x1 : p.x0;
+  const int cs = from1 ? p.c1 : p.c0;
+  const int coff = from1 ? ch - p.c0 : ch;
+  float scale[8], shift[8];
+  {
+    float gm[8], bt[8];
+    load8(p.gamma + ch, gm);
+    load8(p.beta + ch, bt);
+    const double cnt = static_cast<double>(p.hw) * p.cpg;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int g = (ch + e) / p.cpg;
+      const double sum = p.ws[(static_cast<long long>(img) * p.groups + g) * 2];
+      const double sq = p.ws[(static_cast<long long>(img) * p.groups + g) * 2 + 1];
+      const double mean = sum / cnt;
+      double var = sq / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+      scale[e] = gm[e] * rstd;
+      shift[e] = bt[e] - static_cast<float>(mean) * scale[e];
+    }
+  }
+  const int pbeg = blockIdx.x * p.pix_per_cta;
+  const int pend = min(p.hw, pbeg + p.pix_per_cta);
+  for (int px = pbeg + threadIdx.y; px < pend; px += blockDim.y) {
+    float v[8];
+    const long long pix = static_cast<long long>(img) * p.hw + px;
+    load8(src + pix * cs + coff, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float y = v[e] * scale[e] + shift[e];
+      if (p.silu) y = y / (1.0f + __expf(-y));
+      v[e] = y;
+    }
+    store8(p.out + pix * p.C + ch, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers (C <= 8*32*LN_MAXV), two-pass variance.
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 6;  // C <= 1536
+
+struct LnParams {
+  const __half* x;
+  long long rows;
+  int c;
+  float eps;
+  const __half* gamma;
+  const __half* beta;
+  __half* out;
+  const __half* add;
+  __half* out2;
+  long long add_row0;
+};
+
+__global__ void layernorm_kernel(const LnParams p) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int V = p.c >> 3;
+  const long long row0 = static_cast<long long>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5);
+  const long long row_stride = static_cast<long long>(gridDim.x) * warps_per_cta;
+  for (long long row = row0; row < p.rows; row += row_stride) {
+    float v[LN_MAXV][8];
+    float sum = 0.f;
+    const __half* src = p.x + row * p.c;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int cv = lane + i * 32;
+      if (cv < V) {
+        load8(src + cv * 8, v[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += v[i][e];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(p.c);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int cv = lane + i * 32;
+      if (cv < V) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = v[i][e] - mean;
+          sq += d * d;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / static_cast<float>(p.c) + p.eps);
+    const bool do_add = p.add != nullptr && row >= p.add_row0;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int cv = lane + i * 32;
+      if (cv < V) {
+        float gm[8], bt[8], y[8];
+        load8(p.gamma + cv * 8, gm);
+        load8(p.beta + cv * 8, bt);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = (v[i][e] - mean) * rstd * gm[e] + bt[e];
+        store8(p.out + row * p.c + cv * 8, y);
+        if (do_add) {
+          float ad[8];
+          const long long r2 = row - p.add_row0;
+          load8(p.add + r2 * p.c + cv * 8, ad);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] += ad[e];
+          store8(p.out2 + r2 * p.c + cv * 8, y);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace mdk
+
+extern "C" int64_t mdk_groupnorm_ws_bytes(int32_t nimg, int32_t groups) {
+  return static_cast<int64_t>(nimg) * groups * 2 * sizeof(double);
+}
+
+extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* stream_) {
+  using namespace mdk;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MDK_REQUIRE(ctx && a && a->x0 && a->out && a->ws && a->gamma && a->beta,
+              "mdk_groupnorm_f16: null argument");
+  const int C = a->c0 + a->c1;
+  MDK_REQUIRE(a->c0 % 8 == 0 && a->c1 % 8 == 0 && C > 0, "mdk_groupnorm_f16: c0=%d c1=%d must be %%8",
+              a->c0, a->c1);
+  MDK_REQUIRE(a->groups > 0 && C % a->groups == 0, "mdk_groupnorm_f16: C=%d not divisible by groups=%d",
+              C, a->groups);
+  MDK_REQUIRE(C / 8 <= 1024, "mdk_groupnorm_f16: C=%d too large", C);
+  MDK_REQUIRE(a->c1 == 0 || a->x1 != nullptr, "mdk_groupnorm_f16: x1 is NULL");
+  GnParams p;
+  p.x0 = static_cast<const __half*>(a->x0);
+  p.x1 = static_cast<const __half*>(a->x1);
+  p.c0 = a->c0;
+  p.c1 = a->c1;
+  p.C = C;
+  p.nimg = a->nimg;
+  p.hw = a->hw;
+  p.groups = a->groups;
+  p.cpg = C / a->groups;
+  p.eps = a->eps;
+  p.gamma = static_cast<const __half*>(a->gamma);
+  p.beta = static_cast<const __half*>(a->beta);
+  p.silu = a->silu;
+  p.out = static_cast<__half*>(a->out);
+  p.ws = static_cast<double*>(a->ws);
+  const int V = C / 8;
+  const int vx = ((V + 31) / 32) * 32;
+  int vy = 512 / vx;
+  if (vy < 1) vy = 1;
+  // enough CTAs to fill the machine a few times over, at least one pixel row of work each
+  int chunks = (ctx->num_sms * 4 + a->nimg - 1) / a->nimg;
+  const int max_chunks = (a->hw + vy - 1) / vy;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  p.pix_per_cta = (a->hw + chunks - 1) / chunks;
+  chunks = (a->hw + p.pix_per_cta - 1) / p.pix_per_cta;
+  MDK_CHECK_CUDA(cudaMemsetAsync(a->ws, 0, mdk_groupnorm_ws_bytes(a->nimg, a->groups), stream));
+  dim3 block(vx, vy);
+  dim3 grid(chunks, a->nimg);
+  gn_stats_kernel<<<grid, block, a->groups * 2 * sizeof(float), stream>>>(p);
+  count_launch();
+  gn_apply_kernel<<<grid, block, 0, stream>>>(p);
+  count_launch();
+  MDK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mdk_layernorm_f16(mdk_ctx* ctx, const mdk_ln_args* a, void* stream_) {
+  using namespace mdk;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MDK_REQUIRE(ctx && a && a->x && a->out && a->gamma && a->beta, "mdk_layernorm_f16: null argument");
+  MDK_REQUIRE(a->c % 8 == 0 && a->c > 0 && a->c <= 8 * 32 * LN_MAXV,
+              "mdk_layernorm_f16: c=%d must be a multiple of 8 and <= %d", a->c, 8 * 32 * LN_MAXV);
+  MDK_REQUIRE((a->add == nullptr) == (a->out2 == nullptr), "mdk_layernorm_f16: add/out2 mismatch");
+  if (a->rows <= 0) return 0;
+  LnParams p;
+  p.x = static_cast<const __half*>(a->x);
+  p.rows = a->rows;
+  p.c = a->c;
+  p.eps = a->eps;
+  p.gamma = static_cast<const __half*>(a->gamma);
+  p.beta = static_cast<const __half*>(a->beta);
+  p.out = static_cast<__half*>(a->out);
+  p.add = static_cast<const __half*>(a->add);
+  p.out2 = static_cast<__half*>(a->out2);
+  p.add_row0 = a->add_row0;
+  const int warps = 8;
+  long long ctas = (a->rows + warps - 1) / warps;
+  const long long cap = static_cast<long long>(ctx->num_sms) * 16;
+  if (ctas > cap) ctas = cap;
+  layernorm_kernel<<<static_cast<unsigned>(ctas), warps * 32, 0, stream>>>(p);
+  count_launch();
+  MDK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

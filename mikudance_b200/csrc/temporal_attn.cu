@@ -1,0 +1,233 @@
+// Temporal attention of the motion module: softmax(Q K^T / sqrt(d)) V over the frame axis at a
+// fixed pixel and head; sequence length f <= 32.  0.1 % of the step's FLOPs — the kernel is bound
+// by HBM traffic (read Q,K,V, write O once), so it is a SIMT kernel with 16-byte vector IO:
+//   * one (batch, pixel, head) problem per QPW-lane group (QPW = pow2 >= f_q), lane = query frame
+//   * K and V rows of the problem staged in shared memory (broadcast reads), scores in registers
+//   * the reference's "(b f) d c -> (b d) f c" transposes become strided addressing
+//   * PE is added to the query only: q += pe_q[frame]  with pe_q = pe @ Wq^T (fp32)
+//
+// Algorithmic bytes per launch: 2 * nb*npix*C * (2*f_q + 2*f_kv) (Q + O over f_q frames, K + V
+// over f_kv frames).
+#include "host_common.h"
+#include "ptx.cuh"
+#include "../../include/mdk.h"
+
+namespace mdk {
+
+struct TattnParams {
+  const __half* q;
+  const __half* kv;
+  const float* pe_q;
+  __half* out;
+  long long q_ld, kv_ld, out_ld;
+  int q_off, k_off, v_off;
+  int nb, f_q, f_kv, f_kv_rank, f_q_offset, npix, heads, d;
+  int qpw;      // lanes per problem (pow2 >= f_q)
+  int dp;       // padded row length in smem (halves)
+  long long nprob;
+  float scale_log2;
+};
+
+template <int FKV_MAX>
+__global__ void temporal_attn_kernel(const TattnParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int ppw = 32 / p.qpw;  // problems per warp
+  const int dv = p.d >> 3;     // 16-byte vectors per head row
+  const int per_prob = 2 * p.f_kv * p.dp;  // halves (K then V)
+  __half* wsm = reinterpret_cast<__half*>(smem_raw) + static_cast<long long>(warp) * ppw * per_prob;
+
+  const long long groups = (p.nprob + ppw - 1) / ppw;
+  for (long long grp = static_cast<long long>(blockIdx.x) * warps + warp; grp < groups;
+       grp += static_cast<long long>(gridDim.x) * warps) {
+    const long long pid0 = grp * ppw;
+    // ---- stage K and V of the warp's problems ----
+    const int nvec = ppw * p.f_kv * dv * 2;
+    for (int idx = lane; idx < nvec; idx += 32) {
+      int t = idx;
+      const int v = t % dv;
+      t /= dv;
+      const int j = t % p.f_kv;
+      t /= p.f_kv;
+      const int which = t & 1;  // 0 = K, 1 = V
+      const int pr = t >> 1;
+      const long long pid = pid0 + pr;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (pid < p.nprob) {
+        const int h = static_cast<int>(pid % p.heads);
+        const long long bp = pid / p.heads;
+        const int px = static_cast<int>(bp % p.npix);
+        const int b = static_cast<int>(bp / p.npix);
+        const int g = j / p.f_kv_rank, fl = j % p.f_kv_rank;
+        const long long row =
+            ((static_cast<long long>(g) * p.nb + b) * p.f_kv_rank + fl) * p.npix + px;
+        val = *reinterpret_cast<const uint4*>(p.kv + row * p.kv_ld + (which ? p.v_off : p.k_off) +
+                                              h * p.d + v * 8);
+      }
+      *reinterpret_cast<uint4*>(wsm + pr * per_prob + which * p.f_kv * p.dp + j * p.dp + v * 8) = val;
+    }
+    __syncwarp();
+
+    const int pr = lane / p.qpw;
+    const int i = lane % p.qpw;
+    const long long pid = pid0 + pr;
+    const bool active = (i < p.f_q) && (pid < p.nprob);
+    if (active) {
+      const int h = static_cast<int>(pid % p.heads);
+      const long long bp = pid / p.heads;
+      const int px = static_cast<int>(bp % p.npix);
+      const int b = static_cast<int>(bp / p.npix);
+      const long long qrow = (static_cast<long long>(b) * p.f_q + i) * p.npix + px;
+      const __half* qptr = p.q + qrow * p.q_ld + p.q_off + h * p.d;
+      const float* peptr =
+          p.pe_q ? p.pe_q + static_cast<long long>(p.f_q_offset + i) * (p.heads * p.d) + h * p.d
+                 : nullptr;
+      const __half* ks = wsm + pr * per_prob;
+      const __half* vs = ks + p.f_kv * p.dp;
+
+      float s[FKV_MAX];
+#pragma unroll
+      for (int j = 0; j < FKV_MAX; ++j) s[j] = 0.f;
+      for (int v = 0; v < dv; ++v) {
+        float qv[8];
+        {
+          uint4 raw = *reinterpret_cast<const uint4*>(qptr + v * 8);
+          const __half2* hq = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f = __half22float2(hq[e]);
+            qv[2 * e] = f.x;
+            qv[2 * e + 1] = f.y;
+          }
+          if (peptr) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) qv[e] += peptr[v * 8 + e];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < FKV_MAX; ++j) {
+          if (j < p.f_kv) {
+            uint4 raw = *reinterpret_cast<const uint4*>(ks + j * p.dp + v * 8);
+            const __half2* hk = reinterpret_cast<const __half2*>(&raw);
+            float a = s[j];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __half22float2(hk[e]);
+              a = fmaf(qv[2 * e], f.x, a);
+              a = fmaf(qv[2 * e + 1], f.y, a);
+            }
+            s[j] = a;
+          }
+        }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < FKV_MAX; ++j)
+        if (j < p.f_kv) mx = fmaxf(mx, s[j]);
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < FKV_MAX; ++j) {
+        if (j < p.f_kv) {
+          s[j] = exp2f((s[j] - mx) * p.scale_log2);
+          l += s[j];
+        }
+      }
+      const float inv = 1.0f / l;
+      __half* optr = p.out + qrow * p.out_ld + h * p.d;
+      for (int v = 0; v < dv; ++v) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < FKV_MAX; ++j) {
+          if (j < p.f_kv) {
+            uint4 raw = *reinterpret_cast<const uint4*>(vs + j * p.dp + v * 8);
+            const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __half22float2(hv[e]);
+              o[2 * e] = fmaf(s[j], f.x, o[2 * e]);
+              o[2 * e + 1] = fmaf(s[j], f.y, o[2 * e + 1]);
+            }
+          }
+        }
+        uint4 pk;
+        pk.x = pack_half2(o[0] * inv, o[1] * inv);
+        pk.y = pack_half2(o[2] * inv, o[3] * inv);
+        pk.z = pack_half2(o[4] * inv, o[5] * inv);
+        pk.w = pack_half2(o[6] * inv, o[7] * inv);
+        *reinterpret_cast<uint4*>(optr + v * 8) = pk;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace mdk
+
+extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void* stream_) {
+  using namespace mdk;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MDK_REQUIRE(ctx && a && a->q && a->kv && a->out, "mdk_temporal_attn_f16: null argument");
+  MDK_REQUIRE(a->d % 8 == 0 && a->d > 0, "mdk_temporal_attn_f16: d=%d must be a multiple of 8", a->d);
+  MDK_REQUIRE(a->f_q >= 1 && a->f_q <= 32 && a->f_kv >= 1 && a->f_kv <= 32,
+              "mdk_temporal_attn_f16: f_q=%d f_kv=%d must be in 1..32 (PE table max_len 32)", a->f_q,
+              a->f_kv);
+  const int f_kv_rank = a->f_kv_rank > 0 ? a->f_kv_rank : a->f_kv;
+  MDK_REQUIRE(a->f_kv % f_kv_rank == 0, "mdk_temporal_attn_f16: f_kv %% f_kv_rank != 0");
+  MDK_REQUIRE(a->q_ld % 8 == 0 && a->kv_ld % 8 == 0 && a->out_ld % 8 == 0 && a->q_off % 8 == 0 &&
+                  a->k_off % 8 == 0 && a->v_off % 8 == 0,
+              "mdk_temporal_attn_f16: leading dimensions / offsets must be multiples of 8");
+  TattnParams p;
+  p.q = static_cast<const __half*>(a->q);
+  p.kv = static_cast<const __half*>(a->kv);
+  p.pe_q = a->pe_q;
+  p.out = static_cast<__half*>(a->out);
+  p.q_ld = a->q_ld;
+  p.kv_ld = a->kv_ld;
+  p.out_ld = a->out_ld;
+  p.q_off = a->q_off;
+  p.k_off = a->k_off;
+  p.v_off = a->v_off;
+  p.nb = a->nb;
+  p.f_q = a->f_q;
+  p.f_kv = a->f_kv;
+  p.f_kv_rank = f_kv_rank;
+  p.f_q_offset = a->f_q_offset;
+  p.npix = a->npix;
+  p.heads = a->heads;
+  p.d = a->d;
+  int qpw = 1;
+  while (qpw < a->f_q) qpw *= 2;
+  p.qpw = qpw;
+  p.dp = a->d + 8;
+  p.nprob = static_cast<long long>(a->nb) * a->npix * a->heads;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  const int ppw = 32 / qpw;
+  const size_t per_warp = static_cast<size_t>(ppw) * 2 * a->f_kv * p.dp * sizeof(__half);
+  int warps = 8;
+  while (warps > 1 && per_warp * warps > 96 * 1024) warps /= 2;
+  const size_t smem = per_warp * warps;
+  MDK_REQUIRE(smem <= 200 * 1024, "mdk_temporal_attn_f16: problem too large for shared memory");
+  const long long groups = (p.nprob + ppw - 1) / ppw;
+  long long ctas = (groups + warps - 1) / warps;
+  const long long cap = static_cast<long long>(ctx->num_sms) * 8;
+  if (ctas > cap) ctas = cap;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_kernel<16>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_kernel<32>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  if (a->f_kv <= 16)
+    temporal_attn_kernel<16><<<static_cast<unsigned>(ctas), warps * 32, smem, stream>>>(p);
+  else
+    temporal_attn_kernel<32><<<static_cast<unsigned>(ctas), warps * 32, smem, stream>>>(p);
+  count_launch();
+  MDK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,374 @@
+"""GPU diagnostics: run one named kernel check and print error statistics (used under gpurun while
+bringing kernels up; the pass/fail versions of these checks live in tests/).  Each check compares
+the sm_100a kernel with a plain PyTorch fp32 computation of the same op on the same inputs.
+
+usage: python scripts/gpu_diag.py <check> [...]     (python scripts/gpu_diag.py list)
+"""
+import math
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mikudance_b200 import ops  # noqa: E402
+
+DEV = torch.device("cuda:0")
+F16 = torch.float16
+
+
+def report(name, got, ref, tol=2e-3):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    rel = (got - ref).norm() / (ref.norm() + 1e-30)
+    bad = ~torch.isfinite(got)
+    ok = bool(rel < tol) and not bool(bad.any())
+    print(f"[{'OK ' if ok else 'BAD'}] {name}: rel_l2={rel.item():.3e} max_abs={err.max().item():.3e} "
+          f"ref_max={ref.abs().max().item():.3e} nonfinite={int(bad.sum())}", flush=True)
+    if not ok and got.dim() == 2:
+        rows_bad = (err > 10 * tol * ref.abs().max()).any(dim=1).nonzero().flatten()
+        cols_bad = (err > 10 * tol * ref.abs().max()).any(dim=0).nonzero().flatten()
+        print(f"      bad rows: n={rows_bad.numel()} first={rows_bad[:16].tolist()} "
+              f"| bad cols: n={cols_bad.numel()} first={cols_bad[:16].tolist()}")
+        print("      got[0,:8]=", got[0, :8].tolist())
+        print("      ref[0,:8]=", ref[0, :8].tolist())
+    return ok
+
+
+def rnd(*shape, scale=1.0, seed=None):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed if seed is not None else (hash(shape) & 0xFFFF))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+# ------------------------------------------------------------------------------------------------
+def check_gemm_basic():
+    ok = True
+    for (M, N, K) in [(128, 256, 64), (256, 256, 128), (389, 320, 320), (1000, 640, 192),
+                      (128, 32, 64), (300, 64, 256), (512, 128, 512), (640, 576, 64),
+                      (4608, 1280, 1280)]:
+        a = rnd(M, K).to(F16)
+        w = rnd(N, K, scale=K ** -0.5).to(F16)
+        out = ops.gemm(a, w)
+        torch.cuda.synchronize()
+        ok &= report(f"gemm M={M} N={N} K={K}", out, a.float() @ w.float().t())
+    return ok
+
+
+def check_gemm_epilogue():
+    ok = True
+    M, N, K = 777, 320, 320
+    a = rnd(M, K).to(F16)
+    w = rnd(N, K, scale=K ** -0.5).to(F16)
+    bias = rnd(N)
+    res = rnd(M, N).to(F16)
+    rb = rnd(5, N)
+    ref = a.float() @ w.float().t()
+    ok &= report("bias", ops.gemm(a, w, bias=bias), ref + bias)
+    ok &= report("bias+res", ops.gemm(a, w, bias=bias, residual=res), ref + bias + res.float())
+    rows = torch.arange(M, device=DEV)
+    ok &= report("row_bias", ops.gemm(a, w, row_bias=rb, row_div=100),
+                 ref + rb[(rows // 100) % 5])
+    # two-source K
+    a1 = rnd(M, 192, seed=5).to(F16)
+    w2 = rnd(N, K + 192, scale=(K + 192) ** -0.5).to(F16)
+    ok &= report("concatK", ops.gemm(a, w2, a1=a1),
+                 torch.cat([a, a1], 1).float() @ w2.float().t())
+    # geglu
+    Nn = 512
+    wg = rnd(Nn, K, scale=K ** -0.5).to(F16)
+    bg = rnd(Nn)
+    full = a.float() @ wg.float().t() + bg
+    # pack: tile t columns [t*256, t*256+128) values, [+128, +256) gates
+    h, g = full[:, :Nn // 2], full[:, Nn // 2:]
+    refg = h * torch.nn.functional.gelu(g)
+    idx = []
+    for t in range(Nn // 256):
+        idx += list(range(t * 128, t * 128 + 128)) + list(range(Nn // 2 + t * 128, Nn // 2 + t * 128 + 128))
+    idx = torch.tensor(idx, device=DEV)
+    ok &= report("geglu", ops.gemm(a, wg[idx].contiguous(), bias=bg[idx].contiguous(), geglu=True), refg)
+    # segments + transposed V
+    nimg, L = 3, 259
+    M2 = nimg * L
+    a2 = rnd(M2, K).to(F16)
+    w3 = rnd(3 * 320, K, scale=K ** -0.5).to(F16)
+    q = torch.empty(M2, 320, dtype=F16, device=DEV)
+    k = torch.empty(M2, 320, dtype=F16, device=DEV)
+    Lp = 264
+    vt = torch.zeros(nimg, 320, Lp, dtype=F16, device=DEV)
+    ops.gemm(a2, w3, outs=[q, k, vt], trans=[False, False, True], trans_rows=L)
+    ref3 = a2.float() @ w3.float().t()
+    ok &= report("seg q", q, ref3[:, :320])
+    ok &= report("seg k", k, ref3[:, 320:640])
+    ok &= report("seg vT", vt[:, :, :L].permute(0, 2, 1).reshape(M2, 320), ref3[:, 640:])
+    return ok
+
+
+def check_conv():
+    ok = True
+    for (nimg, h, w, cin, cout) in [(2, 16, 16, 64, 64), (3, 24, 24, 128, 64), (5, 12, 12, 320, 320),
+                                    (2, 32, 32, 320, 640), (9, 8, 8, 64, 128), (2, 96, 96, 64, 32),
+                                    (2, 4, 4, 128, 128), (1, 16, 16, 8, 320), (2, 16, 16, 320, 8)]:
+        x = rnd(nimg, h, w, cin).to(F16)
+        wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5).to(F16)
+        bias = rnd(cout)
+        wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+        out = ops.gemm(x.reshape(-1, cin), wp, bias=bias, conv=(nimg, h, w))
+        ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).float(), wt.float(), bias, padding=1)
+        ok &= report(f"conv n={nimg} {h}x{w} {cin}->{cout}", out,
+                     ref.permute(0, 2, 3, 1).reshape(-1, cout))
+    # two-source conv (skip concat)
+    nimg, h, w, c0, c1, cout = 2, 16, 16, 128, 64, 64
+    x0 = rnd(nimg, h, w, c0).to(F16)
+    x1 = rnd(nimg, h, w, c1, seed=3).to(F16)
+    wt = rnd(cout, c0 + c1, 3, 3, scale=(9 * (c0 + c1)) ** -0.5).to(F16)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    out = ops.gemm(x0.reshape(-1, c0), wp, a1=x1.reshape(-1, c1), conv=(nimg, h, w))
+    ref = torch.nn.functional.conv2d(torch.cat([x0, x1], -1).permute(0, 3, 1, 2).float(), wt.float(),
+                                     padding=1)
+    ok &= report("conv concat", out, ref.permute(0, 2, 3, 1).reshape(-1, cout))
+    # stride 2 through im2col
+    nimg, h, w, cin, cout = 2, 16, 16, 64, 64
+    x = rnd(nimg, h, w, cin).to(F16)
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5).to(F16)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    col = ops.im2col3x3(x.reshape(-1, cin), nimg, h, w, 2)
+    out = ops.gemm(col, wp)
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).float(), wt.float(), stride=2, padding=1)
+    ok &= report("conv stride2 (im2col)", out, ref.permute(0, 2, 3, 1).reshape(-1, cout))
+    return ok
+
+
+def check_norms():
+    ok = True
+    for (nimg, hw, c0, c1, silu, eps) in [(3, 256, 320, 0, True, 1e-5), (2, 1024, 640, 320, True, 1e-5),
+                                          (4, 144, 1280, 640, False, 1e-6), (2, 64, 64, 0, True, 1e-5),
+                                          (2, 9216, 320, 0, True, 1e-5)]:
+        C_ = c0 + c1
+        x0 = (rnd(nimg * hw, c0) * 2 + 0.5).to(F16)
+        x1 = (rnd(nimg * hw, c1, seed=9) * 0.7 - 0.3).to(F16) if c1 else None
+        gm = (1 + 0.1 * rnd(C_)).to(F16)
+        bt = (0.1 * rnd(C_, seed=4)).to(F16)
+        out = ops.groupnorm(x0, gm, bt, nimg=nimg, hw=hw, groups=32, eps=eps, silu=silu, x1=x1)
+        xx = torch.cat([x0, x1], 1) if c1 else x0
+        xr = xx.float().reshape(nimg, hw, C_).permute(0, 2, 1)
+        ref = torch.nn.functional.group_norm(xr, 32, gm.float(), bt.float(), eps)
+        if silu:
+            ref = torch.nn.functional.silu(ref)
+        ok &= report(f"groupnorm n={nimg} hw={hw} c={c0}+{c1}", out, ref.permute(0, 2, 1).reshape(-1, C_))
+    for (rows, c) in [(1000, 320), (517, 640), (300, 1280), (64, 64)]:
+        x = (rnd(rows, c) * 1.5 + 0.2).to(F16)
+        gm = (1 + 0.1 * rnd(c)).to(F16)
+        bt = (0.1 * rnd(c, seed=4)).to(F16)
+        ref = torch.nn.functional.layer_norm(x.float(), (c,), gm.float(), bt.float(), 1e-5)
+        ok &= report(f"layernorm {rows}x{c}", ops.layernorm(x, gm, bt), ref)
+        r0 = rows // 2
+        add = rnd(rows - r0, c, seed=8).to(F16)
+        o1, o2 = ops.layernorm(x, gm, bt, add=add, add_row0=r0)
+        ok &= report(f"layernorm+bank {rows}x{c}", o2, ref[r0:] + add.float())
+        ok &= report(f"layernorm(+bank) out1", o1, ref)
+    return ok
+
+
+def ref_temporal(q, k, v, pe_q, nb, f, npix, heads, d):
+    C_ = heads * d
+    qf = q.float().reshape(nb, f, npix, C_)
+    if pe_q is not None:
+        qf = qf + pe_q[:f].reshape(1, f, 1, C_)
+    def sp(t):
+        return t.reshape(nb, -1, npix, heads, d).permute(0, 2, 3, 1, 4)  # b p h f d
+    qh, kh, vh = sp(qf), sp(k.float().reshape(nb, -1, npix, C_)), sp(v.float().reshape(nb, -1, npix, C_))
+    o = torch.nn.functional.scaled_dot_product_attention(qh, kh, vh)
+    return o.permute(0, 3, 1, 2, 4).reshape(nb * f * npix, C_)
+
+
+def check_temporal():
+    ok = True
+    for (nb, f, npix, heads, d) in [(2, 16, 144, 8, 40), (2, 4, 64, 8, 8), (1, 30, 36, 8, 80),
+                                    (2, 32, 16, 8, 160), (2, 7, 50, 4, 16)]:
+        C_ = heads * d
+        qkv = rnd(nb * f * npix, 3 * C_).to(F16)
+        pe = rnd(32, C_, seed=1) * 0.5
+        out = ops.temporal_attention(qkv, nb=nb, f_q=f, npix=npix, heads=heads, d=d, pe_q=pe)
+        ref = ref_temporal(qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:], pe, nb, f, npix, heads, d)
+        ok &= report(f"temporal nb={nb} f={f} npix={npix} h={heads} d={d}", out, ref)
+    # sharded layout: 2 "ranks" x f_local frames gathered
+    nb, f, npix, heads, d = 2, 8, 40, 8, 40
+    C_ = heads * d
+    qkv = rnd(nb * f * npix, 3 * C_).to(F16)
+    pe = rnd(32, C_, seed=1) * 0.5
+    full = ops.temporal_attention(qkv, nb=nb, f_q=f, npix=npix, heads=heads, d=d, pe_q=pe)
+    fl = f // 2
+    q5 = qkv.reshape(nb, f, npix, 3 * C_)
+    gathered = torch.stack([q5[:, r * fl:(r + 1) * fl] for r in range(2)], 0).contiguous()  # [G, nb, fl, npix, 3C]
+    for r in range(2):
+        ql = q5[:, r * fl:(r + 1) * fl].contiguous().reshape(-1, 3 * C_)
+        o = ops.temporal_attention(ql, nb=nb, f_q=fl, npix=npix, heads=heads, d=d, pe_q=pe,
+                                   kv=gathered.reshape(-1, 3 * C_), f_kv=f, f_kv_rank=fl,
+                                   f_q_offset=r * fl, kv_offsets=(C_, 2 * C_))
+        ref = full.reshape(nb, f, npix, C_)[:, r * fl:(r + 1) * fl].reshape(-1, C_)
+        ok &= report(f"temporal sharded rank{r}", o, ref, tol=1e-6)
+    return ok
+
+
+def check_misc():
+    ok = True
+    nimg, h, w, c = 3, 6, 10, 64
+    x = rnd(nimg * h * w, c).to(F16)
+    up = ops.upsample2x(x, nimg, h, w)
+    ref = torch.nn.functional.interpolate(x.float().reshape(nimg, h, w, c).permute(0, 3, 1, 2),
+                                          scale_factor=2.0, mode="nearest")
+    ok &= report("upsample2x", up, ref.permute(0, 2, 3, 1).reshape(-1, c), tol=1e-7)
+    # latents -> nhwc, accumulate, cfg+ddim
+    F_, hh, ww = 6, 8, 8
+    lat = rnd(1, 4, F_, hh, ww).to(F16)
+    idx = torch.tensor([4, 5, 0, 1], dtype=torch.int32, device=DEV)
+    nh = ops.latents_to_nhwc(lat, b=2, frame_idx=idx, fl=4, cpad=8)
+    ref = lat[:, :, idx.long()].repeat(2, 1, 1, 1, 1).permute(0, 2, 3, 4, 1).reshape(-1, 4)
+    ok &= report("latents_to_nhwc", nh[:, :4], ref, tol=1e-7)
+    ok &= report("latents_to_nhwc pad", nh[:, 4:] + 1, torch.ones_like(nh[:, 4:]), tol=1e-7)
+    acc = torch.zeros(2, 4, F_, hh, ww, device=DEV)
+    cnt = torch.zeros(F_, device=DEV)
+    pred = rnd(2 * 4 * hh * ww, 8, seed=2).to(F16)
+    ops.pred_accumulate(pred, acc, cnt, frame_idx=idx, fl=4)
+    ops.pred_accumulate(pred, acc, cnt, frame_idx=None, fl=4)
+    racc = torch.zeros_like(acc)
+    p5 = pred[:, :4].float().reshape(2, 4, hh, ww, 4).permute(0, 4, 1, 2, 3)
+    racc[:, :, idx.long()] += p5
+    racc[:, :, :4] += p5
+    rcnt = torch.zeros(F_, device=DEV)
+    rcnt[idx.long()] += 1
+    rcnt[:4] += 1
+    ok &= report("pred_accumulate", acc.reshape(-1, 1), racc.reshape(-1, 1), tol=1e-7)
+    ok &= report("counter", cnt.reshape(-1, 1), rcnt.reshape(-1, 1), tol=1e-7)
+    coef = torch.tensor([0.8, 0.6, 0.9, math.sqrt(1 - 0.81)], device=DEV)
+    lat2 = lat.clone()
+    ops.cfg_ddim_step(acc, cnt.clamp(min=1), lat2, coef, 3.5, True)
+    e = racc / rcnt.clamp(min=1).reshape(1, 1, F_, 1, 1)
+    g = e[0:1] + 3.5 * (e[1:2] - e[0:1])
+    xf = lat.float()
+    x0 = 0.8 * xf - 0.6 * g
+    ee = 0.8 * g + 0.6 * xf
+    ok &= report("cfg_ddim", lat2.reshape(-1, 1), (0.9 * x0 + coef[3] * ee).reshape(-1, 1), tol=1e-3)
+    # time embedding
+    dim, edim, nrows = 320, 1280, 4000
+    w1 = rnd(edim, dim, scale=dim ** -0.5).to(F16)
+    b1 = (0.1 * rnd(edim)).to(F16)
+    w2 = rnd(edim, edim, scale=edim ** -0.5).to(F16)
+    b2 = (0.1 * rnd(edim, seed=2)).to(F16)
+    pw = rnd(nrows, edim, scale=edim ** -0.5).to(F16)
+    pb = 0.1 * rnd(nrows, seed=3)
+    t = torch.tensor([949], dtype=torch.int64, device=DEV)
+    scratch = torch.empty(2 * edim + dim, device=DEV)
+    out = torch.empty(nrows, device=DEV)
+    ops.time_embed(t, w1, b1, w2, b2, pw, pb, flip_sin_to_cos=True, freq_shift=0.0, scratch=scratch,
+                   out=out)
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, device=DEV, dtype=torch.float32) / half)
+    arg = 949.0 * freqs
+    emb = torch.cat([torch.cos(arg), torch.sin(arg)])
+    h1 = torch.nn.functional.silu(w1.float() @ emb + b1.float())
+    h2 = torch.nn.functional.silu(w2.float() @ h1 + b2.float())
+    ok &= report("time_embed", out.reshape(-1, 1), (pw.float() @ h2 + pb).reshape(-1, 1), tol=1e-4)
+    return ok
+
+
+def ref_attention(q, k, vt, nimg, lq, lkv, heads, d, kv_div):
+    C_ = heads * d
+    qh = q.float().reshape(nimg, lq, heads, d).permute(0, 2, 1, 3)
+    kidx = torch.arange(nimg, device=q.device) // kv_div
+    kh = k.float().reshape(-1, lkv, heads, d)[kidx].permute(0, 2, 1, 3)
+    vh = vt.float()[:, :, :lkv].reshape(-1, heads, d, lkv)[kidx].permute(0, 1, 3, 2)
+    o = torch.nn.functional.scaled_dot_product_attention(qh, kh, vh)
+    return o.permute(0, 2, 1, 3).reshape(nimg * lq, C_)
+
+
+def check_attn():
+    ok = True
+    for (nimg, lq, lkv, heads, d, kv_div) in [(2, 128, 128, 8, 64, 1), (2, 256, 256, 8, 40, 1),
+                                              (3, 144, 144, 8, 160, 1), (4, 576, 257, 8, 80, 2),
+                                              (2, 1024, 1024, 8, 40, 1), (2, 64, 64, 8, 8, 1),
+                                              (2, 16, 16, 8, 32, 1), (1, 2304, 2304, 8, 80, 1)]:
+        C_ = heads * d
+        nkv = nimg // kv_div
+        q = rnd(nimg * lq, C_).to(F16)
+        k = rnd(nkv * lkv, C_, seed=11).to(F16)
+        lp = (lkv + 7) // 8 * 8
+        vt = torch.zeros(nkv, C_, lp, dtype=F16, device=DEV)
+        vt[:, :, :lkv] = rnd(nkv, C_, lkv, seed=12).to(F16)
+        out = ops.attention(q, k, vt, nimg=nimg, lq=lq, lkv=lkv, heads=heads, d=d, kv_div=kv_div)
+        torch.cuda.synchronize()
+        ok &= report(f"attn n={nimg} lq={lq} lkv={lkv} h={heads} d={d}", out,
+                     ref_attention(q, k, vt, nimg, lq, lkv, heads, d, kv_div))
+    return ok
+
+
+def perf_gemm():
+    for (M, N, K, conv) in [(294912, 320, 320, None), (73728, 640, 640, None), (18432, 1280, 1280, None),
+                            (294912, 2560, 320, None), (18432, 1280, 5120, None),
+                            (294912, 320, 320, (32, 96, 96)), (73728, 640, 640, (32, 48, 48)),
+                            (18432, 1280, 1280, (32, 24, 24))]:
+        kk = K * (9 if conv else 1)
+        a = rnd(M, K).to(F16)
+        w = rnd(N, kk, scale=kk ** -0.5).to(F16)
+        out = torch.empty(M, N, dtype=F16, device=DEV)
+        ms = timeit(lambda: ops.gemm(a, w, conv=conv, out=out))
+        fl = 2.0 * M * N * kk
+        print(f"perf {'conv' if conv else 'gemm'} M={M} N={N} K={kk}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s",
+              flush=True)
+    return True
+
+
+def perf_attn():
+    for (nimg, l, heads, d) in [(8, 9216, 8, 40), (32, 2304, 8, 80), (32, 576, 8, 160)]:
+        C_ = heads * d
+        q = rnd(nimg * l, C_).to(F16)
+        k = rnd(nimg * l, C_, seed=11).to(F16)
+        vt = rnd(nimg, C_, l, seed=12).to(F16)
+        out = torch.empty_like(q)
+        ms = timeit(lambda: ops.attention(q, k, vt, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out),
+                    iters=5, warm=2)
+        fl = 4.0 * nimg * heads * l * l * d
+        print(f"perf attn n={nimg} L={l} d={d}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+    return True
+
+
+CHECKS = {
+    "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
+    "norms": check_norms, "temporal": check_temporal, "misc": check_misc, "attn": check_attn,
+    "perf_gemm": perf_gemm, "perf_attn": perf_attn,
+}
+
+if __name__ == "__main__":
+    names = sys.argv[1:]
+    if names == ["list"] or not names:
+        print(" ".join(CHECKS))
+        sys.exit(0)
+    allok = True
+    for n in names:
+        t0 = time.time()
+        try:
+            r = CHECKS[n]()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(f"[EXC] {n}: {type(e).__name__}: {e}", flush=True)
+            r = False
+        print(f"== {n}: {'PASS' if r else 'FAIL'} ({time.time() - t0:.1f}s)", flush=True)
+        allok &= bool(r)
+    sys.exit(0 if allok else 1)
