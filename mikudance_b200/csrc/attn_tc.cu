@@ -1,0 +1,382 @@
+// Flash-style attention on tcgen05 for sm_100a (spatial self-attention with reference-feature
+// K/V, CLIP cross-attention).  One CTA = one (image, head, 128-query tile); 192 threads:
+//   warp 0   : TMA producer — Q once, then K / V^T tiles through a KST-stage ring
+//   warp 1   : MMA issuer   — S_j = Q K_j^T (TMEM, double buffered), O += P_j V_j (TMEM)
+//   warps 2-5: softmax      — one query row per thread: tcgen05.ld S_j, online softmax in the
+//                             exp2 domain with a lazy rescale of O (only when the running max grows
+//                             by more than 2^8, so P stays <= 256 in fp16), P_j -> shared memory in
+//                             the 128B-swizzled K-major layout, final O / l epilogue
+// All MMA operands are K-major 128B-swizzled tiles (same descriptors as the GEMM): Q [128 x d],
+// K [BKV x d] loaded through a 4-D tensor map [d, heads, L, image] whose out-of-bounds fill zero-pads
+// d to a multiple of 16 and L to the tile; V is consumed as V^T [d x BKV] (emitted transposed by the
+// K/V projection GEMM), so P V needs no MN-major operand.
+//
+// Algorithmic FLOPs per launch: 4 * nimg * heads * lq * lkv * d.
+#include "host_common.h"
+#include "ptx.cuh"
+#include "../../include/mdk.h"
+
+namespace mdk {
+
+constexpr int ATT_BQ = 128;
+constexpr int ATT_THREADS = 192;
+constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmV;
+  __half* out;
+  long long ldo;
+  int lq, lkv, heads, d;
+  int dk16;  // ceil(d / 16): K steps of Q K^T
+  int dn;    // ceil16(d): N of the P V MMA
+  int kv_div;
+  int n_kv_tiles;
+  float scale_log2;
+};
+
+template <int NCH, int BKV, int KST>
+struct AttnCfg {
+  static constexpr int Q_BYTES = NCH * ATT_BQ * 128;
+  static constexpr int K_STAGE = NCH * BKV * 128;
+  static constexpr int V_CHUNK = NCH * 64 * 128;  // up to 64*NCH rows of 128 B per 64-wide kv chunk
+  static constexpr int V_STAGE = (BKV / 64) * V_CHUNK;
+  static constexpr int P_BYTES = (BKV / 64) * ATT_BQ * 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + KST * (K_STAGE + V_STAGE) + P_BYTES + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr uint32_t S_COL0 = 0, S_COL1 = 128, O_COL = 256;
+};
+
+template <int NCH, int BKV, int KST>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = AttnCfg<NCH, BKV, KST>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + KST * Cfg::K_STAGE;
+  uint8_t* sP = sV + KST * Cfg::V_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_bar = bars;                    // [1]
+  uint64_t* kv_full = bars + 1;              // [KST]
+  uint64_t* kv_empty = bars + 1 + KST;       // [KST]
+  uint64_t* s_full = bars + 1 + 2 * KST;     // [2]
+  uint64_t* p_full = bars + 3 + 2 * KST;     // [1]
+  uint64_t* pv_done = bars + 4 + 2 * KST;    // [1]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5 + 2 * KST);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int kvimg = img / p.kv_div;
+  const int n_tiles = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_bar, 1);
+    for (int s = 0; s < KST; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 4);  // one arrive per softmax warp
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      mbar_expect_tx(q_bar, Cfg::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        tma_load_4d(sQ + c * ATT_BQ * 128, &p.tmQ, q_bar, c * 64, head, q0, img);
+      const uint32_t stage_bytes =
+          static_cast<uint32_t>(Cfg::K_STAGE + (BKV / 64) * p.dn * 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1u);
+        mbar_expect_tx(&kv_full[stage], stage_bytes);
+        const int kv0 = j * BKV;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          tma_load_4d(sK + stage * Cfg::K_STAGE + c * BKV * 128, &p.tmK, &kv_full[stage], c * 64,
+                      head, kv0, kvimg);
+#pragma unroll
+        for (int c = 0; c < BKV / 64; ++c)
+          tma_load_3d(sV + stage * Cfg::V_STAGE + c * Cfg::V_CHUNK, &p.tmV, &kv_full[stage],
+                      kv0 + c * 64, head * p.d, kvimg);
+        if (++stage == KST) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc_s = make_idesc_f16(ATT_BQ, BKV);
+    const uint32_t idesc_o = make_idesc_f16(ATT_BQ, static_cast<uint32_t>(p.dn));
+    const uint32_t tS[2] = {tmem_base + Cfg::S_COL0, tmem_base + Cfg::S_COL1};
+    const uint32_t tO = tmem_base + Cfg::O_COL;
+    auto issue_s = [&](int stage, int buf) {
+      if (lane == 0) {
+        for (int ks = 0; ks < p.dk16; ++ks) {
+          const int c = ks >> 2, w = ks & 3;
+          const uint64_t adesc = make_sdesc_sw128(smem_u32(sQ + c * ATT_BQ * 128)) + 2u * w;
+          const uint64_t bdesc =
+              make_sdesc_sw128(smem_u32(sK + stage * Cfg::K_STAGE + c * BKV * 128)) + 2u * w;
+          tc_mma_f16_ss(tS[buf], adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(&s_full[buf]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      // look ahead: S_{j+1} while the softmax warps work on S_j
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == KST) {
+        nstage = 0;
+        nphase ^= 1u;
+      }
+      if (j + 1 < n_tiles) {
+        mbar_wait(&kv_full[nstage], nphase);
+        tc_fence_after();
+        issue_s(nstage, (j + 1) & 1);
+      }
+      mbar_wait(p_full, static_cast<uint32_t>(j & 1));
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          const int c = ks >> 2, w = ks & 3;
+          const uint64_t adesc = make_sdesc_sw128(smem_u32(sP + c * ATT_BQ * 128)) + 2u * w;
+          const uint64_t bdesc =
+              make_sdesc_sw128(smem_u32(sV + stage * Cfg::V_STAGE + c * Cfg::V_CHUNK)) + 2u * w;
+          tc_mma_f16_ss(tO, adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc_commit(&kv_empty[stage]);
+        tc_commit(pv_done);
+      }
+      __syncwarp();
+      stage = nstage;
+      phase = nphase;
+    }
+  } else {
+    // ======================= softmax / correction / epilogue warps =======================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS[2] = {tmem_base + lane_off + Cfg::S_COL0, tmem_base + lane_off + Cfg::S_COL1};
+    const uint32_t tO = tmem_base + lane_off + Cfg::O_COL;
+    float m_used = -INFINITY;  // reference max (scaled, log2 domain) the exponentials are taken against
+    float l_sum = 0.f;
+    uint8_t* prow = sP + row * 128;
+    const int sw = row & 7;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&s_full[buf], static_cast<uint32_t>((j >> 1) & 1));
+      tc_fence_after();
+      uint32_t v[BKV / 32][32];
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) tmem_ld_x32(tS[buf] + c * 32, v[c]);
+      tmem_wait_ld();
+      const int nvalid = p.lkv - j * BKV;  // columns >= nvalid are padding
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float x = __uint_as_float(v[c][e]);
+          if (c * 32 + e >= nvalid) x = -INFINITY;
+          v[c][e] = __float_as_uint(x);
+          mx = fmaxf(mx, x);
+        }
+      }
+      mx *= p.scale_log2;
+      float alpha = 1.0f;
+      bool rescale = false;
+      if (j == 0) {
+        m_used = mx;
+      } else if (mx > m_used + ATT_RESCALE_THRESHOLD) {
+        alpha = ex2_approx(m_used - mx);
+        m_used = mx;
+        l_sum *= alpha;
+        rescale = true;
+      }
+      uint32_t pk[BKV / 2];
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][e]), p.scale_log2, -m_used));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][e + 1]), p.scale_log2, -m_used));
+          rs += p0 + p1;
+          pk[(c * 32 + e) >> 1] = pack_half2(p0, p1);
+        }
+      }
+      l_sum += rs;
+      // P_{j-1} V_{j-1} must have retired before P (single buffer) or O may be touched
+      if (j > 0) {
+        mbar_wait(pv_done, static_cast<uint32_t>((j - 1) & 1));
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, rescale)) {
+        for (int c = 0; c < p.dn; c += 16) {
+          uint32_t o[16];
+          tmem_ld_x16(tO + c, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+          tmem_st_x16(tO + c, o);
+        }
+        tmem_wait_st();
+      }
+      // P -> smem, K-major, 128B swizzle: 16-byte piece q of row r lands at piece (q ^ (r & 7))
+#pragma unroll
+      for (int cc = 0; cc < BKV / 64; ++cc) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4 val;
+          val.x = pk[cc * 32 + q * 4 + 0];
+          val.y = pk[cc * 32 + q * 4 + 1];
+          val.z = pk[cc * 32 + q * 4 + 2];
+          val.w = pk[cc * 32 + q * 4 + 3];
+          *reinterpret_cast<uint4*>(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4)) = val;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l ----
+    mbar_wait(pv_done, static_cast<uint32_t>((n_tiles - 1) & 1));
+    tc_fence_after();
+    const float inv = 1.0f / l_sum;
+    const int qrow = q0 + row;
+    __half* dst = p.out + (static_cast<long long>(blockIdx.z) * p.lq + qrow) * p.ldo + head * p.d;
+    for (int c = 0; c < p.dn; c += 16) {
+      uint32_t o[16];
+      tmem_ld_x16(tO + c, o);
+      tmem_wait_ld();
+      if (qrow < p.lq) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (c + q * 8 < p.d) {
+            uint4 val;
+            val.x = pack_half2(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+            val.y = pack_half2(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+            val.z = pack_half2(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+            val.w = pack_half2(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c + q * 8) = val;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int NCH, int BKV, int KST>
+static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a,
+                       cudaStream_t stream) {
+  using Cfg = AttnCfg<NCH, BKV, KST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<NCH, BKV, KST>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const uint64_t d = static_cast<uint64_t>(a->d);
+  {
+    uint64_t dims[4] = {d, static_cast<uint64_t>(a->heads), static_cast<uint64_t>(a->lq),
+                        static_cast<uint64_t>(a->nimg)};
+    uint64_t str[4] = {0, d * 2, static_cast<uint64_t>(a->ldq) * 2,
+                       static_cast<uint64_t>(a->ldq) * 2 * a->lq};
+    uint32_t box[4] = {64, 1, ATT_BQ, 1};
+    if (encode_tmap_f16(&p.tmQ, a->q, 4, dims, str, box)) return -1;
+  }
+  {
+    uint64_t dims[4] = {d, static_cast<uint64_t>(a->heads), static_cast<uint64_t>(a->lkv),
+                        static_cast<uint64_t>(a->nkv)};
+    uint64_t str[4] = {0, d * 2, static_cast<uint64_t>(a->ldk) * 2,
+                       static_cast<uint64_t>(a->ldk) * 2 * a->lkv};
+    uint32_t box[4] = {64, 1, BKV, 1};
+    if (encode_tmap_f16(&p.tmK, a->k, 4, dims, str, box)) return -1;
+  }
+  {
+    const uint64_t C = d * a->heads;
+    uint64_t dims[3] = {static_cast<uint64_t>(a->lkv), C, static_cast<uint64_t>(a->nkv)};
+    uint64_t str[3] = {0, static_cast<uint64_t>(a->ldvt) * 2, static_cast<uint64_t>(a->ldvt) * 2 * C};
+    uint32_t box[3] = {64, static_cast<uint32_t>(p.dn), 1};
+    if (encode_tmap_f16(&p.tmV, a->vt, 3, dims, str, box)) return -1;
+  }
+  p.n_kv_tiles = (a->lkv + BKV - 1) / BKV;
+  dim3 grid((a->lq + ATT_BQ - 1) / ATT_BQ, a->heads, a->nimg);
+  attn_tc_kernel<NCH, BKV, KST><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  count_launch();
+  MDK_CHECK_CUDA(cudaGetLastError());
+  (void)ctx;
+  return 0;
+}
+
+}  // namespace mdk
+
+extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stream_) {
+  using namespace mdk;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MDK_REQUIRE(ctx && a && a->q && a->k && a->vt && a->out, "mdk_attn_fwd_f16: null argument");
+  MDK_REQUIRE(a->d % 8 == 0 && a->d >= 8 && a->d <= 192, "mdk_attn_fwd_f16: d=%d unsupported", a->d);
+  MDK_REQUIRE(a->lq > 0 && a->lkv > 0 && a->heads > 0 && a->nimg > 0 && a->nkv > 0 && a->kv_div > 0,
+              "mdk_attn_fwd_f16: empty problem");
+  MDK_REQUIRE(a->heads <= 65535 && a->nimg <= 65535, "mdk_attn_fwd_f16: grid too large");
+  MDK_REQUIRE((a->nimg + a->kv_div - 1) / a->kv_div <= a->nkv, "mdk_attn_fwd_f16: nkv too small");
+  MDK_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldvt % 8 == 0 && a->ldo % 8 == 0,
+              "mdk_attn_fwd_f16: leading dimensions must be multiples of 8");
+  MDK_REQUIRE(a->ldvt >= a->lkv, "mdk_attn_fwd_f16: ldvt < lkv");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = static_cast<__half*>(a->out);
+  p.ldo = a->ldo;
+  p.lq = a->lq;
+  p.lkv = a->lkv;
+  p.heads = a->heads;
+  p.d = a->d;
+  p.dk16 = (a->d + 15) / 16;
+  p.dn = p.dk16 * 16;
+  p.kv_div = a->kv_div;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  if (a->d <= 64) return launch_attn<1, 128, 3>(ctx, p, a, stream);
+  if (a->d <= 128) return launch_attn<2, 128, 2>(ctx, p, a, stream);
+  return launch_attn<3, 64, 2>(ctx, p, a, stream);
+}

@@ -1,0 +1,225 @@
+"""Synthetic (random-init) weights and inputs for benchmarks and parity tests.
+
+There are no trained checkpoints in this environment, so bench.py / tests / smoke() use a
+deterministic random-init state dict with the reference's exact key set and shapes (the contract of
+`UNet3DConditionModel.state_dict()`, src/models/unet_3d_mix.py of the reference) — every tensor is
+seeded by its own name, so the oracle, the reference modules and the CUDA path can all be fed
+identical weights without sharing any construction order.  Motion-module `proj_out` is NOT
+zero-initialised here (the reference zero-inits it at construction, src/models/motion_module.py:73-76,
+which would turn the temporal path into the identity and hide it from parity tests).
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from typing import Dict, List, Tuple
+
+import torch
+
+SD15_CONFIG = dict(
+    in_channels=4, out_channels=4, flip_sin_to_cos=True, freq_shift=0,
+    block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, norm_num_groups=32, norm_eps=1e-5,
+    cross_attention_dim=768, attention_head_dim=8, motion_heads=8, pe_max_len=32,
+)
+TINY_CONFIG = dict(SD15_CONFIG, block_out_channels=(64, 128, 256, 256), cross_attention_dim=64)
+
+
+def block_plan(cfg) -> dict:
+    """Static block structure (src/models/unet_3d_mix.py:124-269, unet_3d_blocks.py:654-655)."""
+    boc = list(cfg["block_out_channels"])
+    lpb = cfg["layers_per_block"]
+    down = []
+    out_c = boc[0]
+    for i in range(len(boc)):
+        in_c, out_c = out_c, boc[i]
+        last = i == len(boc) - 1
+        down.append(dict(idx=i, in_c=in_c, out_c=out_c, layers=lpb, attn=not last, downsample=not last))
+    rev = list(reversed(boc))
+    up = []
+    out_c = rev[0]
+    for i in range(len(boc)):
+        prev_out = out_c
+        out_c = rev[i]
+        in_c = rev[min(i + 1, len(boc) - 1)]
+        res_in = []
+        for j in range(lpb + 1):
+            res_skip = in_c if j == lpb else out_c
+            res_inp = prev_out if j == 0 else out_c
+            res_in.append((res_inp, res_skip))
+        up.append(dict(idx=i, out_c=out_c, res_in=res_in, attn=i > 0, upsample=i < len(boc) - 1))
+    return dict(down=down, mid_c=boc[-1], up=up)
+
+
+def positional_encoding(max_len: int, d_model: int) -> torch.Tensor:
+    """PositionalEncoding buffer `pe` [1, max_len, d_model] (src/models/motion_module.py:275-286)."""
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(1, max_len, d_model)
+    pe[0, :, 0::2] = torch.sin(position * div_term)
+    pe[0, :, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def state_dict_spec(cfg) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """[(key, shape, kind)] for every tensor of the reference UNet3DConditionModel state dict.
+    kind: 'w' weight (fan-in = prod(shape[1:])), 'b' bias, 'g' norm gain, 'pe' buffer."""
+    boc = cfg["block_out_channels"]
+    c0 = boc[0]
+    temb = 4 * c0
+    ctxd = cfg["cross_attention_dim"]
+    spec: List[Tuple[str, Tuple[int, ...], str]] = []
+
+    def norm(p, c):
+        spec.append((p + ".weight", (c,), "g"))
+        spec.append((p + ".bias", (c,), "b"))
+
+    def lin(p, o, i, bias=True):
+        spec.append((p + ".weight", (o, i), "w"))
+        if bias:
+            spec.append((p + ".bias", (o,), "b"))
+
+    def conv(p, o, i, k):
+        spec.append((p + ".weight", (o, i, k, k), "w"))
+        spec.append((p + ".bias", (o,), "b"))
+
+    def resnet(p, cin, cout):
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cout, cin, 3)
+        lin(p + ".time_emb_proj", cout, temb)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + ".conv_shortcut", cout, cin, 1)
+
+    def ff(p, c):
+        lin(p + ".net.0.proj", 8 * c, c)
+        lin(p + ".net.2", c, 4 * c)
+
+    def attn(p, c, kv):
+        lin(p + ".to_q", c, c, bias=False)
+        lin(p + ".to_k", c, kv, bias=False)
+        lin(p + ".to_v", c, kv, bias=False)
+        lin(p + ".to_out.0", c, c)
+
+    def spatial(p, c):
+        norm(p + ".norm", c)
+        conv(p + ".proj_in", c, c, 1)
+        b = p + ".transformer_blocks.0"
+        attn(b + ".attn1", c, c)
+        norm(b + ".norm1", c)
+        attn(b + ".attn2", c, ctxd)
+        norm(b + ".norm2", c)
+        ff(b + ".ff", c)
+        norm(b + ".norm3", c)
+        conv(p + ".proj_out", c, c, 1)
+
+    def motion(p, c):
+        t = p + ".temporal_transformer"
+        norm(t + ".norm", c)
+        lin(t + ".proj_in", c, c)
+        b = t + ".transformer_blocks.0"
+        for a in range(2):
+            attn(b + f".attention_blocks.{a}", c, c)
+            spec.append((b + f".attention_blocks.{a}.pos_encoder.pe", (1, cfg["pe_max_len"], c), "pe"))
+            norm(b + f".norms.{a}", c)
+        ff(b + ".ff", c)
+        norm(b + ".ff_norm", c)
+        lin(t + ".proj_out", c, c)
+
+    conv("conv_in", c0, cfg["in_channels"], 3)
+    lin("time_embedding.linear_1", temb, c0)
+    lin("time_embedding.linear_2", temb, temb)
+    plan = block_plan(cfg)
+    for d in plan["down"]:
+        p = f"down_blocks.{d['idx']}"
+        for j in range(d["layers"]):
+            resnet(f"{p}.resnets.{j}", d["in_c"] if j == 0 else d["out_c"], d["out_c"])
+            if d["attn"]:
+                spatial(f"{p}.attentions.{j}", d["out_c"])
+            motion(f"{p}.motion_modules.{j}", d["out_c"])
+        if d["downsample"]:
+            conv(f"{p}.downsamplers.0.conv", d["out_c"], d["out_c"], 3)
+    mc = plan["mid_c"]
+    resnet("mid_block.resnets.0", mc, mc)
+    spatial("mid_block.attentions.0", mc)
+    motion("mid_block.motion_modules.0", mc)
+    resnet("mid_block.resnets.1", mc, mc)
+    for u in plan["up"]:
+        p = f"up_blocks.{u['idx']}"
+        for j, (ci, cs) in enumerate(u["res_in"]):
+            resnet(f"{p}.resnets.{j}", ci + cs, u["out_c"])
+            if u["attn"]:
+                spatial(f"{p}.attentions.{j}", u["out_c"])
+            motion(f"{p}.motion_modules.{j}", u["out_c"])
+        if u["upsample"]:
+            conv(f"{p}.upsamplers.0.conv", u["out_c"], u["out_c"], 3)
+    norm("conv_norm_out", c0)
+    conv("conv_out", cfg["out_channels"], c0, 3)
+    return spec
+
+
+def _seeded_randn(name: str, shape, seed: int) -> torch.Tensor:
+    g = torch.Generator(device="cpu")
+    g.manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+    return torch.randn(shape, generator=g, dtype=torch.float32)
+
+
+def synthetic_state_dict(cfg, seed: int = 0, dtype=torch.float16) -> Dict[str, torch.Tensor]:
+    """Deterministic random-init weights with the reference's key set (values rounded to `dtype`)."""
+    sd = {}
+    for name, shape, kind in state_dict_spec(cfg):
+        if kind == "w":
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            t = _seeded_randn(name, shape, seed) / math.sqrt(fan_in)
+        elif kind == "g":
+            t = 1.0 + 0.1 * _seeded_randn(name, shape, seed)
+        elif kind == "b":
+            t = 0.02 * _seeded_randn(name, shape, seed)
+        else:
+            # the reference casts this buffer with the model (.to(fp16)); keep the key fp32 but put the
+            # values on the `dtype` grid so fp32 oracle and fp16 model see the same table
+            t = positional_encoding(shape[1], shape[2]).to(dtype).float()
+        sd[name] = t.to(dtype) if kind != "pe" else t
+    return sd
+
+
+def reader_bank_order(cfg) -> List[Tuple[str, int, int]]:
+    """[(attention module path, channels, downscale)] in the order ReferenceAttentionControl pairs
+    reader and writer blocks (src/models/mutual_mix_attention.py:292-302,346-354)."""
+    plan = block_plan(cfg)
+    n = len(cfg["block_out_channels"])
+    names = []
+    for d in plan["down"]:
+        if d["attn"]:
+            for j in range(d["layers"]):
+                names.append((f"down_blocks.{d['idx']}.attentions.{j}", d["out_c"], 2 ** d["idx"]))
+    for u in plan["up"]:
+        if u["attn"]:
+            for j in range(len(u["res_in"])):
+                names.append((f"up_blocks.{u['idx']}.attentions.{j}", u["out_c"], 2 ** (n - 1 - u["idx"])))
+    names.append(("mid_block.attentions.0", plan["mid_c"], 2 ** (n - 1)))
+    names.sort(key=lambda t: -t[1])
+    return names
+
+
+def synthetic_banks(cfg, n_img: int, h: int, w: int, seed: int = 102, scale: float = 1.0,
+                    dtype=torch.float16) -> Dict[str, torch.Tensor]:
+    """Stand-in for the reference-UNet output: one [n_img, hw, C] feature bank per spatial block
+    (SURVEY.md §8d).  Rounded to fp16 like ReferenceAttentionControl.update does (:353)."""
+    banks = {}
+    for i, (name, c, ds) in enumerate(reader_bank_order(cfg)):
+        hw = (h // ds) * (w // ds)
+        banks[name] = (scale * _seeded_randn(f"bank{i}", (n_img, hw, c), seed)).to(dtype)
+    return banks
+
+
+def synthetic_inputs(cfg, b: int, f: int, h: int, w: int, lctx: int = 257, seed: int = 100):
+    """latents [b, 4, f, h, w] and encoder_hidden_states [b, lctx, ctx_dim]; the first batch entry of
+    the context is zeros when b == 2 (uncond branch, src/pipelines/pipeline_mikudance.py:418-423)."""
+    sample = _seeded_randn("latents", (1, cfg["in_channels"], f, h, w), seed).repeat(b, 1, 1, 1, 1)
+    ctx = _seeded_randn("ctx", (1, lctx, cfg["cross_attention_dim"]), seed + 1)
+    if b == 2:
+        ctx = torch.cat([torch.zeros_like(ctx), ctx], dim=0)
+    return sample, ctx

@@ -1,0 +1,2 @@
+"""`src.models.attention` of the reference -> mikudance_b200.unet_3d."""
+from mikudance_b200.unet_3d import TemporalBasicTransformerBlock  # noqa: F401

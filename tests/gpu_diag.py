@@ -349,7 +349,67 @@ def perf_attn():
     return True
 
 
+def build_model(cfg, seed=0):
+    from mikudance_b200 import synth
+    from mikudance_b200.unet_3d import UNet3DConditionModel
+    m = UNet3DConditionModel(block_out_channels=cfg["block_out_channels"],
+                             cross_attention_dim=cfg["cross_attention_dim"], use_inflated_groupnorm=True,
+                             use_motion_module=True, motion_module_mid_block=True,
+                             motion_module_type="Vanilla",
+                             motion_module_kwargs=dict(temporal_position_encoding=True,
+                                                       temporal_position_encoding_max_len=32),
+                             unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+    sd = synth.synthetic_state_dict(cfg, seed=seed)
+    m.load_state_dict(sd)
+    return m.to(device=DEV, dtype=F16).eval(), sd
+
+
+def unet_check(cfg, B, f, h, w, lctx, t, with_banks=True, tag=""):
+    from mikudance_b200 import synth
+    from mikudance_b200.reference_control import ReferenceAttentionControl
+    from oracle import unet3d_oracle as O
+    t0 = time.time()
+    m, sd = build_model(cfg)
+    x, ctx = synth.synthetic_inputs(cfg, B, f, h, w, lctx=lctx)
+    banks = synth.synthetic_banks(cfg, B * f, h, w) if with_banks else None
+    ReferenceAttentionControl(m, mode="read", do_classifier_free_guidance=(B == 2), fusion_blocks="full")
+    if with_banks:
+        for blk, (name, c, ds) in zip(m.spatial_blocks(), synth.reader_bank_order(cfg)):
+            blk.bank = [banks[name].to(DEV)]
+    eng = m.engine()
+    eng.trace = {}
+    y = m(x.to(DEV, F16), torch.tensor(t), encoder_hidden_states=ctx.to(DEV, F16), return_dict=False)[0]
+    torch.cuda.synchronize()
+    t1 = time.time()
+    otr = {}
+    sd32 = {k: v.float() for k, v in sd.items()}
+    with torch.no_grad():
+        yo = O.unet3d_forward(sd32, cfg, x.half().float(), t, ctx.half().float(), banks=banks,
+                              cfg_guidance=(B == 2), trace=otr)
+    print(f"   gpu {t1 - t0:.1f}s oracle {time.time() - t1:.1f}s")
+    ok = True
+    for key, (tt, N, hh, ww) in eng.trace.items():
+        ref = otr[key].permute(0, 2, 3, 1).reshape(N * hh * ww, -1)
+        ok &= report(f"{tag} trace {key}", tt.cpu(), ref, tol=2e-2)
+    ok &= report(f"{tag} unet output", y.cpu().reshape(-1, 1), yo.reshape(-1, 1), tol=2e-2)
+    return ok
+
+
+def check_unet_tiny():
+    from mikudance_b200 import synth
+    ok = unet_check(synth.TINY_CONFIG, 2, 4, 16, 16, 9, 949, True, "tiny")
+    ok &= unet_check(synth.TINY_CONFIG, 1, 3, 8, 24, 5, 19, False, "tiny-nobank")
+    return ok
+
+
+def check_unet_a():
+    """BASELINE config A: SD-1.5 sized UNet, 256x256 (32x32 latents), 4 frames, CFG."""
+    from mikudance_b200 import synth
+    return unet_check(synth.SD15_CONFIG, 2, 4, 32, 32, 257, 499, True, "cfgA")
+
+
 CHECKS = {
+    "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
     "norms": check_norms, "temporal": check_temporal, "misc": check_misc, "attn": check_attn,
     "perf_gemm": perf_gemm, "perf_attn": perf_attn,
