@@ -1,0 +1,153 @@
+"""DenoiseLoop — the hot path itself: the per-step body of MikuDanceVideoPipeline.__call__
+(src/pipelines/pipeline_mikudance.py:573-686 of the reference) as one CUDA graph per clip:
+
+    zero accumulators -> for each context window: gather latents (NHWC) -> UNet3D forward ->
+    scatter-add prediction -> [all-reduce over frame shards] -> window average + CFG + DDIM update
+
+Everything step-dependent (timestep, DDIM coefficients) is read from device memory, so the same
+captured graph is replayed for every step; per step the host only writes 1 + 4 scalars.
+
+Frame sharding: rank r of G runs the UNet on frames [r*fl, (r+1)*fl) of every window (both CFG
+branches); the motion modules all-gather K/V over NCCL (engine._motion); the window accumulators are
+summed across ranks once per step (2.4 MB at 768x768x16f) and the DDIM update is replicated.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import ops
+from .context import get_context_scheduler
+
+F16 = torch.float16
+
+
+class DenoiseLoop:
+    def __init__(self, unet, scheduler, guidance_scale: float = 3.5, context_schedule: str = "uniform",
+                 context_frames: int = 30, context_stride: int = 1, context_overlap: int = 8,
+                 process_group=None, use_cuda_graph: bool = True):
+        self.unet = unet
+        self.eng = unet.engine()
+        self.dev = self.eng.dev
+        self.scheduler = scheduler
+        self.guidance_scale = float(guidance_scale)
+        self.do_cfg = guidance_scale > 1.0                      # pipeline_mikudance.py:397
+        self.ctx_sched = get_context_scheduler(context_schedule)
+        self.context_frames, self.context_stride, self.context_overlap = (
+            context_frames, context_stride, context_overlap)
+        self.pg = process_group
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+            self.rank = dist.get_rank(process_group)
+        else:
+            self.world, self.rank = 1, 0
+        self.eng.set_process_group(process_group, self.rank, self.world)
+        self.use_graph = use_cuda_graph
+        self.graph = None
+        self._pin_t = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._pin_coef = torch.zeros(4, dtype=torch.float32).pin_memory()
+
+    # ------------------------------------------------------------------------------------------
+    def prepare(self, latents: torch.Tensor, ctx: torch.Tensor, num_inference_steps: int,
+                banks_for_window: Optional[Callable[[List[int]], Optional[Dict[str, torch.Tensor]]]] = None):
+        """latents [1, 4, F, h, w] (device, fp16, updated in place by step());
+        ctx [2, L, D] = [uncond; cond] (or [1, L, D] without guidance);
+        banks_for_window(window) -> {attention path: [(nb * len(window)) , hw, C]} full-window banks
+        (the stand-in for / output of the reference UNet; this rank slices its frames)."""
+        dev = self.dev
+        assert latents.is_cuda and latents.dtype == F16 and latents.is_contiguous()
+        self.latents = latents
+        _, self.c, self.F, self.h, self.w = latents.shape
+        self.nb = 2 if self.do_cfg else 1
+        self.ctx = ctx.to(device=dev, dtype=F16).contiguous()
+        self.scheduler.set_timesteps(num_inference_steps)
+        self.timesteps = [int(t) for t in self.scheduler.timesteps]
+        # the reference always calls the scheduler with step=0 (pipeline_mikudance.py:603-612)
+        self.windows = list(self.ctx_sched(0, num_inference_steps, self.F, self.context_frames,
+                                           self.context_stride, self.context_overlap))
+        self.win = []
+        for wdw in self.windows:
+            L = len(wdw)
+            if L % self.world != 0:
+                raise ValueError(f"a window of {L} frames cannot be split evenly over {self.world} GPUs; "
+                                 "choose context_frames divisible by the GPU count")
+            fl = L // self.world
+            lo = self.rank * fl
+            idx = torch.tensor(wdw[lo:lo + fl], dtype=torch.int32, device=dev)
+            banks = None
+            if banks_for_window is not None:
+                full = banks_for_window(wdw)
+                if full is not None:
+                    banks = {}
+                    for k, v in full.items():
+                        hw, C = v.shape[-2], v.shape[-1]
+                        v = v.reshape(self.nb, L, hw, C)[:, lo:lo + fl].reshape(self.nb * fl, hw, C)
+                        banks[k] = v.to(device=dev, dtype=F16).contiguous()
+            self.win.append(dict(frames=wdw, idx=idx, fl=fl, f_off=lo, L=L, banks=banks))
+        self.acc = torch.zeros((self.nb, self.c, self.F, self.h, self.w), dtype=torch.float32, device=dev)
+        self.counter = torch.zeros(self.F, dtype=torch.float32, device=dev)
+        self.coef = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.vpred = self.scheduler.config.prediction_type == "v_prediction"
+        self.graph = None
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    def _step_body(self):
+        eng = self.eng
+        self.acc.zero_()
+        self.counter.zero_()
+        n_unc_all = self.do_cfg
+        for wd in self.win:
+            fl = wd["fl"]
+            x_in = ops.latents_to_nhwc(self.latents, b=self.nb, frame_idx=wd["idx"], fl=fl,
+                                       cpad=eng.cin_pad)
+            pred = eng.run(x_in, self.nb, fl, self.h, self.w, self.ctx, wd["banks"],
+                           n_uncond=(fl if n_unc_all else 0), f_off=wd["f_off"], f_total=wd["L"])
+            ops.pred_accumulate(pred, self.acc, self.counter, frame_idx=wd["idx"], fl=fl)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.acc, group=self.pg)
+            dist.all_reduce(self.counter, group=self.pg)
+        ops.cfg_ddim_step(self.acc, self.counter, self.latents, self.coef, self.guidance_scale,
+                          self.vpred)
+
+    def _set_step_scalars(self, t: int):
+        coef, _ = self.scheduler.step_coefficients(t)
+        self._pin_t[0] = t
+        self._pin_coef.copy_(coef)
+        self.eng.t_dev.copy_(self._pin_t, non_blocking=True)
+        self.coef.copy_(self._pin_coef, non_blocking=True)
+
+    def capture(self):
+        """Warm up once eagerly (kernel attributes, allocator, NCCL), restore the latents, capture."""
+        saved = self.latents.clone()
+        self._set_step_scalars(self.timesteps[0])
+        self._step_body()
+        torch.cuda.synchronize(self.dev)
+        self.latents.copy_(saved)
+        if self.use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body()
+            self.graph = g
+            self.latents.copy_(saved)
+        torch.cuda.synchronize(self.dev)
+
+    def step(self, i: int):
+        """One DDIM step (all windows); latents are updated in place."""
+        self._set_step_scalars(self.timesteps[i])
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+
+    def run(self, callback=None, callback_steps: int = 1):
+        if self.graph is None and self.use_graph:
+            self.capture()
+        for i, t in enumerate(self.timesteps):
+            self.step(i)
+            if callback is not None and i % callback_steps == 0:
+                callback(i, t, self.latents)
+        return self.latents

@@ -16,6 +16,49 @@ from ._lib import (AttnArgs, GemmArgs, GnArgs, LnArgs, TattnArgs, TembArgs, chec
 F16 = torch.float16
 
 
+class Profiler:
+    """CUDA-event timing of every kernel launch issued through this module (bench.py's roofline
+    pass; never active inside a timed region or a graph capture)."""
+
+    def __init__(self):
+        self.records = []   # (kind, flops, bytes, ev0, ev1)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(kind, dict(n=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["n"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        for d in out.values():
+            if d["ms"] > 0:
+                d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12
+                d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        return out
+
+
+_PROF: Optional[Profiler] = None
+
+
+def set_profiler(p: Optional[Profiler]) -> None:
+    global _PROF
+    _PROF = p
+
+
+def _run(kind: str, flops: float, nbytes: float, fn, what: str) -> None:
+    if _PROF is None:
+        check(fn(), what)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(), what)
+    e1.record()
+    _PROF.records.append((kind, flops, nbytes, e0, e1))
+
+
 def _chk16(t: torch.Tensor, name: str) -> None:
     if t.dtype != F16 or not t.is_cuda:
         raise TypeError(f"{name}: expected a CUDA float16 tensor, got {t.dtype} on {t.device}")
@@ -90,7 +133,9 @@ def gemm(a0: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None
             else:
                 args.ldo[s] = o.stride(0)
         ret = outs
-    check(lib.mdk_gemm_f16(get_ctx(dev), C.byref(args), cur_stream(dev)), "mdk_gemm_f16")
+    ktot = (9 if conv is not None else 1) * (k0 + k1)
+    _run("gemm_tc", 2.0 * M * N * ktot, 2.0 * (M * (k0 + k1) + N * ktot + M * n_out * (2 if residual is not None else 1)),
+         lambda: lib.mdk_gemm_f16(get_ctx(dev), C.byref(args), cur_stream(dev)), "mdk_gemm_f16")
     return ret
 
 
@@ -108,8 +153,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, nimg: int, 
     a.nimg, a.nkv, a.kv_div = nimg, vt.shape[0], kv_div
     a.lq, a.lkv, a.heads, a.d = lq, lkv, heads, d
     a.scale = scale if scale is not None else 1.0 / math.sqrt(d)
-    check(load_library().mdk_attn_fwd_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
-          "mdk_attn_fwd_f16")
+    _run("attn_tc", 4.0 * nimg * heads * lq * lkv * d, 2.0 * heads * d * (2 * nimg * lq + 2 * vt.shape[0] * lkv),
+         lambda: load_library().mdk_attn_fwd_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
+         "mdk_attn_fwd_f16")
     return out
 
 
@@ -141,8 +187,10 @@ def temporal_attention(qkv: torch.Tensor, *, nb: int, f_q: int, npix: int, heads
     a.out, a.out_ld = ptr(out), out.stride(0)
     a.nb, a.f_q, a.f_q_offset, a.npix, a.heads, a.d = nb, f_q, f_q_offset, npix, heads, d
     a.scale = 1.0 / math.sqrt(d)
-    check(load_library().mdk_temporal_attn_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
-          "mdk_temporal_attn_f16")
+    fkv = a.f_kv
+    _run("temporal_attn", 4.0 * nb * npix * heads * f_q * fkv * d, 2.0 * nb * npix * Cc * (2 * f_q + 2 * fkv),
+         lambda: load_library().mdk_temporal_attn_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
+         "mdk_temporal_attn_f16")
     return out
 
 
@@ -164,8 +212,9 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, nimg
     a.nimg, a.hw, a.groups, a.eps = nimg, hw, groups, eps
     a.gamma, a.beta, a.silu = ptr(gamma), ptr(beta), 1 if silu else 0
     a.out, a.ws = ptr(out), ptr(ws)
-    check(load_library().mdk_groupnorm_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
-          "mdk_groupnorm_f16")
+    _run("groupnorm", 0.0, 3.0 * 2 * nimg * hw * (c0 + c1),
+         lambda: load_library().mdk_groupnorm_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
+         "mdk_groupnorm_f16")
     return out
 
 
@@ -186,8 +235,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
         if out2 is None:
             out2 = torch.empty_like(add)
         a.add, a.out2, a.add_row0 = ptr(add), ptr(out2), add_row0
-    check(load_library().mdk_layernorm_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
-          "mdk_layernorm_f16")
+    _run("layernorm", 0.0, 2.0 * rows * c * (2 if add is None else 3),
+         lambda: load_library().mdk_layernorm_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
+         "mdk_layernorm_f16")
     return (out, out2) if add is not None else out
 
 
@@ -195,8 +245,9 @@ def upsample2x(x: torch.Tensor, nimg: int, h: int, w: int) -> torch.Tensor:
     _chk16(x, "x")
     c = x.shape[1]
     out = torch.empty((nimg * 4 * h * w, c), dtype=F16, device=x.device)
-    check(load_library().mdk_upsample2x_f16(get_ctx(x.device), ptr(x), ptr(out), nimg, h, w, c,
-                                            cur_stream(x.device)), "mdk_upsample2x_f16")
+    _run("upsample2x", 0.0, 2.0 * 5 * nimg * h * w * c,
+         lambda: load_library().mdk_upsample2x_f16(get_ctx(x.device), ptr(x), ptr(out), nimg, h, w, c,
+                                                   cur_stream(x.device)), "mdk_upsample2x_f16")
     return out
 
 
@@ -206,8 +257,9 @@ def im2col3x3(x: torch.Tensor, nimg: int, h: int, w: int, stride: int) -> torch.
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
     kpad = 9 * c
     out = torch.empty((nimg * ho * wo, kpad), dtype=F16, device=x.device)
-    check(load_library().mdk_im2col3x3_f16(get_ctx(x.device), ptr(x), ptr(out), nimg, h, w, c,
-                                           stride, kpad, cur_stream(x.device)), "mdk_im2col3x3_f16")
+    _run("im2col", 0.0, 2.0 * (nimg * h * w * c + out.numel()),
+         lambda: load_library().mdk_im2col3x3_f16(get_ctx(x.device), ptr(x), ptr(out), nimg, h, w, c,
+                                                  stride, kpad, cur_stream(x.device)), "mdk_im2col3x3_f16")
     return out
 
 
@@ -221,8 +273,9 @@ def time_embed(timestep: torch.Tensor, w1, b1, w2, b2, proj_w, proj_b, *, flip_s
     a.w1, a.b1, a.w2, a.b2, a.edim = ptr(w1), ptr(b1), ptr(w2), ptr(b2), w1.shape[0]
     a.proj_w, a.proj_b, a.nrows = ptr(proj_w), ptr(proj_b), (proj_w.shape[0] if proj_w is not None else 0)
     a.scratch, a.temb_out = ptr(scratch), ptr(out)
-    check(load_library().mdk_time_embed_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
-          "mdk_time_embed_f16")
+    _run("time_embed", 0.0, 2.0 * (w1.numel() + w2.numel() + (proj_w.numel() if proj_w is not None else 0)),
+         lambda: load_library().mdk_time_embed_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
+         "mdk_time_embed_f16")
     return out
 
 
@@ -233,9 +286,10 @@ def latents_to_nhwc(sample: torch.Tensor, *, b: int, frame_idx: Optional[torch.T
     assert sample.is_contiguous()
     b_src, c, F, h, w = sample.shape
     out = torch.empty((b * fl * h * w, cpad), dtype=F16, device=sample.device)
-    check(load_library().mdk_latents_to_nhwc(get_ctx(sample.device), ptr(sample), ptr(out), b, b_src,
-                                             c, F, ptr(frame_idx), fl, h * w, cpad,
-                                             cur_stream(sample.device)), "mdk_latents_to_nhwc")
+    _run("latent_glue", 0.0, 2.0 * out.numel(),
+         lambda: load_library().mdk_latents_to_nhwc(get_ctx(sample.device), ptr(sample), ptr(out), b,
+                                                    b_src, c, F, ptr(frame_idx), fl, h * w, cpad,
+                                                    cur_stream(sample.device)), "mdk_latents_to_nhwc")
     return out
 
 
@@ -244,9 +298,11 @@ def pred_accumulate(pred: torch.Tensor, acc: torch.Tensor, counter: Optional[tor
     """pred [(b fl) hw, cpad] fp16;  acc [b, c, F, h, w] fp32 +=;  counter [F] fp32 += 1"""
     b, c, F, h, w = acc.shape
     assert acc.dtype == torch.float32 and acc.is_contiguous()
-    check(load_library().mdk_pred_accumulate(get_ctx(pred.device), ptr(pred), ptr(acc), ptr(counter),
-                                             b, c, F, ptr(frame_idx), fl, h * w, pred.shape[1],
-                                             cur_stream(pred.device)), "mdk_pred_accumulate")
+    _run("latent_glue", 0.0, 2.0 * pred.numel() + 8.0 * b * c * fl * h * w,
+         lambda: load_library().mdk_pred_accumulate(get_ctx(pred.device), ptr(pred), ptr(acc),
+                                                    ptr(counter), b, c, F, ptr(frame_idx), fl, h * w,
+                                                    pred.shape[1], cur_stream(pred.device)),
+         "mdk_pred_accumulate")
 
 
 def cfg_ddim_step(acc: torch.Tensor, counter: torch.Tensor, latents: torch.Tensor,
@@ -255,7 +311,8 @@ def cfg_ddim_step(acc: torch.Tensor, counter: torch.Tensor, latents: torch.Tenso
     nb, c, F, h, w = acc.shape
     _chk16(latents, "latents")
     assert latents.is_contiguous() and coef.dtype == torch.float32 and coef.numel() == 4
-    check(load_library().mdk_cfg_ddim_step(get_ctx(acc.device), ptr(acc), ptr(counter), ptr(latents),
-                                           ptr(coef), float(guidance_scale), nb, c, F, h * w,
-                                           1 if v_prediction else 0, cur_stream(acc.device)),
-          "mdk_cfg_ddim_step")
+    _run("cfg_ddim", 0.0, 4.0 * acc.numel() + 4.0 * latents.numel(),
+         lambda: load_library().mdk_cfg_ddim_step(get_ctx(acc.device), ptr(acc), ptr(counter),
+                                                  ptr(latents), ptr(coef), float(guidance_scale), nb, c,
+                                                  F, h * w, 1 if v_prediction else 0,
+                                                  cur_stream(acc.device)), "mdk_cfg_ddim_step")
