@@ -319,7 +319,56 @@ def check_attn():
     return ok
 
 
+def warm_gpu(seconds=1.5):
+    """spin the GPU so the clocks leave idle before anything is timed"""
+    a = torch.randn(8192, 8192, device=DEV, dtype=F16)
+    t0 = time.time()
+    while time.time() - t0 < seconds:
+        for _ in range(10):
+            a @ a
+        torch.cuda.synchronize()
+
+
+def timeit_ms(fn, min_ms=60.0):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    one = timeit(fn, iters=3, warm=0)
+    iters = max(5, int(min_ms / max(one, 1e-3)))
+    return timeit(fn, iters=iters, warm=0)
+
+
+def ncu_gemm():
+    """a few launches for an ncu capture: L0 square linear (HBM-bound) and L0 3x3 conv"""
+    M, N, K = 294912, 320, 320
+    a = rnd(M, K).to(F16)
+    w = rnd(N, K, scale=K ** -0.5).to(F16)
+    out = torch.empty(M, N, dtype=F16, device=DEV)
+    w9 = rnd(N, 9 * K, scale=(9 * K) ** -0.5).to(F16)
+    warm_gpu(1.0)
+    for _ in range(3):
+        ops.gemm(a, w, out=out)
+        ops.gemm(a, w9, conv=(32, 96, 96), out=out)
+    torch.cuda.synchronize()
+    return True
+
+
+def ncu_attn():
+    nimg, l, heads, d = 2, 9216, 8, 40
+    C_ = heads * d
+    q = rnd(nimg * l, C_).to(F16)
+    k = rnd(nimg * l, C_, seed=11).to(F16)
+    vt = rnd(nimg, C_, l, seed=12).to(F16)
+    out = torch.empty_like(q)
+    warm_gpu(1.0)
+    for _ in range(2):
+        ops.attention(q, k, vt, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out)
+    torch.cuda.synchronize()
+    return True
+
+
 def perf_gemm():
+    warm_gpu()
     for (M, N, K, conv) in [(294912, 320, 320, None), (73728, 640, 640, None), (18432, 1280, 1280, None),
                             (294912, 2560, 320, None), (18432, 1280, 5120, None),
                             (294912, 320, 320, (32, 96, 96)), (73728, 640, 640, (32, 48, 48)),
@@ -328,7 +377,7 @@ def perf_gemm():
         a = rnd(M, K).to(F16)
         w = rnd(N, kk, scale=kk ** -0.5).to(F16)
         out = torch.empty(M, N, dtype=F16, device=DEV)
-        ms = timeit(lambda: ops.gemm(a, w, conv=conv, out=out))
+        ms = timeit_ms(lambda: ops.gemm(a, w, conv=conv, out=out))
         fl = 2.0 * M * N * kk
         print(f"perf {'conv' if conv else 'gemm'} M={M} N={N} K={kk}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s",
               flush=True)
@@ -336,14 +385,14 @@ def perf_gemm():
 
 
 def perf_attn():
+    warm_gpu()
     for (nimg, l, heads, d) in [(8, 9216, 8, 40), (32, 2304, 8, 80), (32, 576, 8, 160)]:
         C_ = heads * d
         q = rnd(nimg * l, C_).to(F16)
         k = rnd(nimg * l, C_, seed=11).to(F16)
         vt = rnd(nimg, C_, l, seed=12).to(F16)
         out = torch.empty_like(q)
-        ms = timeit(lambda: ops.attention(q, k, vt, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out),
-                    iters=5, warm=2)
+        ms = timeit_ms(lambda: ops.attention(q, k, vt, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out))
         fl = 4.0 * nimg * heads * l * l * d
         print(f"perf attn n={nimg} L={l} d={d}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
     return True
@@ -412,7 +461,7 @@ CHECKS = {
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
     "norms": check_norms, "temporal": check_temporal, "misc": check_misc, "attn": check_attn,
-    "perf_gemm": perf_gemm, "perf_attn": perf_attn,
+    "perf_gemm": perf_gemm, "perf_attn": perf_attn, "ncu_gemm": ncu_gemm, "ncu_attn": ncu_attn,
 }
 
 if __name__ == "__main__":
