@@ -294,7 +294,7 @@ def main():
     if not args.skip_profile:
         prof = ops.Profiler()
         ops.set_profiler(prof)
-        loop._set_step_scalars(loop.timesteps[0])
+        loop._set_step_scalars(0)
         loop._step_body()
         torch.cuda.synchronize(dev)
         ops.set_profiler(None)

@@ -19,6 +19,7 @@ import torch
 
 from . import ops
 from .context import get_context_scheduler
+from .sharding import shard_window, slice_bank
 
 F16 = torch.float16
 
@@ -46,8 +47,6 @@ class DenoiseLoop:
         self.eng.set_process_group(process_group, self.rank, self.world)
         self.use_graph = use_cuda_graph
         self.graph = None
-        self._pin_t = torch.zeros(1, dtype=torch.int64).pin_memory()
-        self._pin_coef = torch.zeros(4, dtype=torch.float32).pin_memory()
 
     # ------------------------------------------------------------------------------------------
     def prepare(self, latents: torch.Tensor, ctx: torch.Tensor, num_inference_steps: int,
@@ -70,25 +69,24 @@ class DenoiseLoop:
         self.win = []
         for wdw in self.windows:
             L = len(wdw)
-            if L % self.world != 0:
-                raise ValueError(f"a window of {L} frames cannot be split evenly over {self.world} GPUs; "
-                                 "choose context_frames divisible by the GPU count")
-            fl = L // self.world
-            lo = self.rank * fl
-            idx = torch.tensor(wdw[lo:lo + fl], dtype=torch.int32, device=dev)
+            mine, lo = shard_window(wdw, self.rank, self.world)
+            fl = len(mine)
+            idx = torch.tensor(mine, dtype=torch.int32, device=dev)
             banks = None
             if banks_for_window is not None:
                 full = banks_for_window(wdw)
                 if full is not None:
-                    banks = {}
-                    for k, v in full.items():
-                        hw, C = v.shape[-2], v.shape[-1]
-                        v = v.reshape(self.nb, L, hw, C)[:, lo:lo + fl].reshape(self.nb * fl, hw, C)
-                        banks[k] = v.to(device=dev, dtype=F16).contiguous()
+                    banks = {k: slice_bank(v, self.nb, L, self.rank, self.world)
+                             .to(device=dev, dtype=F16).contiguous() for k, v in full.items()}
             self.win.append(dict(frames=wdw, idx=idx, fl=fl, f_off=lo, L=L, banks=banks))
         self.acc = torch.zeros((self.nb, self.c, self.F, self.h, self.w), dtype=torch.float32, device=dev)
         self.counter = torch.zeros(self.F, dtype=torch.float32, device=dev)
         self.coef = torch.zeros(4, dtype=torch.float32, device=dev)
+        # per-step scalars live in device tables; step() moves row i into the buffers the captured
+        # graph reads (stream-ordered D2D copies: no host buffer is reused while a copy is in flight)
+        self.t_table = torch.tensor(self.timesteps, dtype=torch.int64, device=dev)
+        self.coef_table = torch.stack([self.scheduler.step_coefficients(t)[0] for t in self.timesteps]
+                                      ).to(device=dev, dtype=torch.float32).contiguous()
         self.vpred = self.scheduler.config.prediction_type == "v_prediction"
         self.graph = None
         return self
@@ -113,17 +111,14 @@ class DenoiseLoop:
         ops.cfg_ddim_step(self.acc, self.counter, self.latents, self.coef, self.guidance_scale,
                           self.vpred)
 
-    def _set_step_scalars(self, t: int):
-        coef, _ = self.scheduler.step_coefficients(t)
-        self._pin_t[0] = t
-        self._pin_coef.copy_(coef)
-        self.eng.t_dev.copy_(self._pin_t, non_blocking=True)
-        self.coef.copy_(self._pin_coef, non_blocking=True)
+    def _set_step_scalars(self, i: int):
+        self.eng.t_dev.copy_(self.t_table[i:i + 1], non_blocking=True)
+        self.coef.copy_(self.coef_table[i], non_blocking=True)
 
     def capture(self):
         """Warm up once eagerly (kernel attributes, allocator, NCCL), restore the latents, capture."""
         saved = self.latents.clone()
-        self._set_step_scalars(self.timesteps[0])
+        self._set_step_scalars(0)
         self._step_body()
         torch.cuda.synchronize(self.dev)
         self.latents.copy_(saved)
@@ -137,7 +132,7 @@ class DenoiseLoop:
 
     def step(self, i: int):
         """One DDIM step (all windows); latents are updated in place."""
-        self._set_step_scalars(self.timesteps[i])
+        self._set_step_scalars(i)
         if self.graph is not None:
             self.graph.replay()
         else:

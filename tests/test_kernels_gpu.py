@@ -1,0 +1,67 @@
+"""GPU (-m gpu): every sm_100a kernel against a plain PyTorch fp32 computation of the same op on the
+same inputs, called through the C ABI (mikudance_b200.ops -> libmikudance_sm100.so).  Tolerance:
+normalised L2 error <= 1e-3 per kernel for fp16 outputs (fp16 epsilon is 9.8e-4; observed 2.1e-4 to
+2.9e-4 = one fp16 rounding of an fp32-accumulated result), exact for pure data movement."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import gpu_diag as D  # noqa: E402  (tests/ is on sys.path under pytest)
+
+
+@pytest.fixture(autouse=True)
+def _strict_tolerance(monkeypatch):
+    orig = D.report
+
+    def strict(name, got, ref, tol=1e-3):
+        return orig(name, got, ref, tol=min(tol, 1e-3))
+    monkeypatch.setattr(D, "report", strict)
+
+
+def test_native_library_is_what_runs():
+    from mikudance_b200 import _lib
+    n0 = _lib.launch_count()
+    a = torch.randn(256, 64, device="cuda").half()
+    w = torch.randn(128, 64, device="cuda").half()
+    D.ops.gemm(a, w)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == n0 + 1
+
+
+def test_gemm_shapes_and_tails():
+    assert D.check_gemm_basic()
+
+
+def test_gemm_fused_epilogues():
+    assert D.check_gemm_epilogue()
+
+
+def test_conv3x3_implicit_gemm():
+    assert D.check_conv()
+
+
+def test_groupnorm_layernorm():
+    assert D.check_norms()
+
+
+def test_temporal_attention_incl_sharded_layout():
+    assert D.check_temporal()
+
+
+def test_glue_kernels_cfg_ddim_time_embed():
+    assert D.check_misc()
+
+
+def test_flash_attention_tcgen05():
+    assert D.check_attn()
+
+
+def test_argument_errors_are_reported():
+    from mikudance_b200 import _lib
+    a = torch.randn(64, 36, device="cuda").half()          # K = 36 is not a multiple of 8
+    w = torch.randn(64, 36, device="cuda").half()
+    with pytest.raises(_lib.MdkError, match="multiples of 8"):
+        D.ops.gemm(a, w)
+    with pytest.raises(TypeError):
+        D.ops.gemm(a.float(), w)
