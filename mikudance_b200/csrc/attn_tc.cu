@@ -1,7 +1,8 @@
 // Flash-style attention on tcgen05 for sm_100a (spatial self-attention with reference-feature
 // K/V, CLIP cross-attention).  One CTA = one (image, head, 128-query tile); 192 threads:
 //   warp 0   : TMA producer — Q once, then K / V^T tiles through a KST-stage ring
-//   warp 1   : MMA issuer   — S_j = Q K_j^T (TMEM, double buffered), O += P_j V_j (TMEM)
+//   warp 1   : MMA issuer   — S_j = Q K_j^T (TMEM), O += P_j V_j (TMEM); S_{j+1} is issued as soon
+//                             as the softmax warps have drained S_j into registers
 //   warps 2-5: softmax      — one query row per thread: tcgen05.ld S_j, online softmax in the
 //                             exp2 domain with a lazy rescale of O (only when the running max grows
 //                             by more than 2^8, so P stays <= 256 in fp16), P_j -> shared memory in
@@ -41,18 +42,26 @@ struct AttnCfg {
   static constexpr int V_CHUNK = NCH * 64 * 128;  // up to 64*NCH rows of 128 B per 64-wide kv chunk
   static constexpr int V_STAGE = (BKV / 64) * V_CHUNK;
   static constexpr int P_BYTES = (BKV / 64) * ATT_BQ * 128;
-  static constexpr int SMEM_BYTES = Q_BYTES + KST * (K_STAGE + V_STAGE) + P_BYTES + 1024 + 256;
-  static constexpr uint32_t TMEM_COLS = 512;
-  static constexpr uint32_t S_COL0 = 0, S_COL1 = 128, O_COL = 256;
+  // dynamic shared memory is declared __align__(1024) (checked at run time), so no alignment slack:
+  // at head_dim <= 64 two CTAs must fit in one SM's 228 KB
+  static constexpr int SMEM_BYTES = Q_BYTES + KST * (K_STAGE + V_STAGE) + P_BYTES + 256;
+  // S (128 x BKV fp32, single buffer: it is drained into registers at the start of each softmax
+  // step) at column 0, O (128 x 64*NCH fp32) at column 128
+  static constexpr uint32_t S_COL = 0, O_COL = 128;
+  static constexpr uint32_t TMEM_COLS = (128 + 64 * NCH <= 256) ? 256 : 512;
+  static constexpr int CTAS_PER_SM = (NCH == 1) ? 2 : 1;
 };
 
 template <int NCH, int BKV, int KST>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, (NCH == 1) ? 2 : 1)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<NCH, BKV, KST>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("mdk attn: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::Q_BYTES;
   uint8_t* sV = sK + KST * Cfg::K_STAGE;
@@ -61,7 +70,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   uint64_t* q_bar = bars;                    // [1]
   uint64_t* kv_full = bars + 1;              // [KST]
   uint64_t* kv_empty = bars + 1 + KST;       // [KST]
-  uint64_t* s_full = bars + 1 + 2 * KST;     // [2]
+  uint64_t* s_full = bars + 1 + 2 * KST;     // [1] S_j complete in TMEM
+  uint64_t* s_free = bars + 2 + 2 * KST;     // [1] S_j drained into registers (4 warp arrivals)
   uint64_t* p_full = bars + 3 + 2 * KST;     // [1]
   uint64_t* pv_done = bars + 4 + 2 * KST;    // [1]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5 + 2 * KST);
@@ -85,8 +95,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);
     mbar_init(p_full, 4);  // one arrive per softmax warp
     mbar_init(pv_done, 1);
     fence_mbar_init();
@@ -130,18 +140,18 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     // ======================= MMA issuer =======================
     const uint32_t idesc_s = make_idesc_f16(ATT_BQ, BKV);
     const uint32_t idesc_o = make_idesc_f16(ATT_BQ, static_cast<uint32_t>(p.dn));
-    const uint32_t tS[2] = {tmem_base + Cfg::S_COL0, tmem_base + Cfg::S_COL1};
+    const uint32_t tS = tmem_base + Cfg::S_COL;
     const uint32_t tO = tmem_base + Cfg::O_COL;
-    auto issue_s = [&](int stage, int buf) {
+    auto issue_s = [&](int stage) {
       if (lane == 0) {
         for (int ks = 0; ks < p.dk16; ++ks) {
           const int c = ks >> 2, w = ks & 3;
           const uint64_t adesc = make_sdesc_sw128(smem_u32(sQ + c * ATT_BQ * 128)) + 2u * w;
           const uint64_t bdesc =
               make_sdesc_sw128(smem_u32(sK + stage * Cfg::K_STAGE + c * BKV * 128)) + 2u * w;
-          tc_mma_f16_ss(tS[buf], adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
+          tc_mma_f16_ss(tS, adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
         }
-        tc_commit(&s_full[buf]);
+        tc_commit(s_full);
       }
       __syncwarp();
     };
@@ -150,9 +160,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     uint32_t phase = 0;
     mbar_wait(&kv_full[0], 0);
     tc_fence_after();
-    issue_s(0, 0);
+    issue_s(0);
     for (int j = 0; j < n_tiles; ++j) {
-      // look ahead: S_{j+1} while the softmax warps work on S_j
+      // look ahead: S_{j+1} as soon as the softmax warps hold S_j in registers
       int nstage = stage + 1;
       uint32_t nphase = phase;
       if (nstage == KST) {
@@ -161,8 +171,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       }
       if (j + 1 < n_tiles) {
         mbar_wait(&kv_full[nstage], nphase);
+        mbar_wait(s_free, static_cast<uint32_t>(j & 1));
         tc_fence_after();
-        issue_s(nstage, (j + 1) & 1);
+        issue_s(nstage);
       }
       mbar_wait(p_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
@@ -187,7 +198,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tS[2] = {tmem_base + lane_off + Cfg::S_COL0, tmem_base + lane_off + Cfg::S_COL1};
+    const uint32_t tS = tmem_base + lane_off + Cfg::S_COL;
     const uint32_t tO = tmem_base + lane_off + Cfg::O_COL;
     float m_used = -INFINITY;  // reference max (scaled, log2 domain) the exponentials are taken against
     float l_sum = 0.f;
@@ -195,13 +206,16 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     const int sw = row & 7;
 
     for (int j = 0; j < n_tiles; ++j) {
-      const int buf = j & 1;
-      mbar_wait(&s_full[buf], static_cast<uint32_t>((j >> 1) & 1));
+      mbar_wait(s_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
       uint32_t v[BKV / 32][32];
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) tmem_ld_x32(tS[buf] + c * 32, v[c]);
+      for (int c = 0; c < BKV / 32; ++c) tmem_ld_x32(tS + c * 32, v[c]);
       tmem_wait_ld();
+      // S_j now lives in registers: the tensor core may overwrite it with S_{j+1}
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
       const int nvalid = p.lkv - j * BKV;  // columns >= nvalid are padding
       float mx = -INFINITY;
 #pragma unroll
@@ -225,19 +239,6 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         l_sum *= alpha;
         rescale = true;
       }
-      uint32_t pk[BKV / 2];
-      float rs = 0.f;
-#pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][e]), p.scale_log2, -m_used));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][e + 1]), p.scale_log2, -m_used));
-          rs += p0 + p1;
-          pk[(c * 32 + e) >> 1] = pack_half2(p0, p1);
-        }
-      }
-      l_sum += rs;
       // P_{j-1} V_{j-1} must have retired before P (single buffer) or O may be touched
       if (j > 0) {
         mbar_wait(pv_done, static_cast<uint32_t>((j - 1) & 1));
@@ -254,19 +255,30 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         }
         tmem_wait_st();
       }
+      // exp2, row sum, fp16 pack and the store of P, 8 columns (one 16-byte piece) at a time.
       // P -> smem, K-major, 128B swizzle: 16-byte piece q of row r lands at piece (q ^ (r & 7))
+      float rs = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < BKV / 64; ++cc) {
+      for (int c = 0; c < BKV / 32; ++c) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint4 val;
-          val.x = pk[cc * 32 + q * 4 + 0];
-          val.y = pk[cc * 32 + q * 4 + 1];
-          val.z = pk[cc * 32 + q * 4 + 2];
-          val.w = pk[cc * 32 + q * 4 + 3];
-          *reinterpret_cast<uint4*>(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4)) = val;
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 =
+                ex2_approx(fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e]), p.scale_log2, -m_used));
+            const float p1 =
+                ex2_approx(fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used));
+            rs += p0 + p1;
+            pk[e] = pack_half2(p0, p1);
+          }
+          const int col8 = c * 4 + q4;        // 8-column piece index inside the BKV tile
+          const int cc = col8 >> 3, q = col8 & 7;
+          *reinterpret_cast<uint4*>(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4)) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
+      l_sum += rs;
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -376,7 +388,7 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
   p.dn = p.dk16 * 16;
   p.kv_div = a->kv_div;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  if (a->d <= 64) return launch_attn<1, 128, 3>(ctx, p, a, stream);
+  if (a->d <= 64) return launch_attn<1, 128, 2>(ctx, p, a, stream);  // 2 CTAs per SM
   if (a->d <= 128) return launch_attn<2, 128, 2>(ctx, p, a, stream);
   return launch_attn<3, 64, 2>(ctx, p, a, stream);
 }
