@@ -202,8 +202,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     const uint32_t tO = tmem_base + lane_off + Cfg::O_COL;
     float m_used = -INFINITY;  // reference max (scaled, log2 domain) the exponentials are taken against
     float l_sum = 0.f;
-    uint8_t* prow = sP + row * 128;
-    const int sw = row & 7;
+    const uint32_t prow = smem_u32(sP) + static_cast<uint32_t>(row) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
 
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, static_cast<uint32_t>(j & 1));
@@ -216,17 +216,21 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
-      const int nvalid = p.lkv - j * BKV;  // columns >= nvalid are padding
+      const int nvalid = p.lkv - j * BKV;  // columns >= nvalid are padding (last tile only)
       float mx = -INFINITY;
+      if (nvalid < BKV) {
+#pragma unroll
+        for (int c = 0; c < BKV / 32; ++c) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (c * 32 + e >= nvalid) v[c][e] = 0xff800000u;  // -inf
+          }
+        }
+      }
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float x = __uint_as_float(v[c][e]);
-          if (c * 32 + e >= nvalid) x = -INFINITY;
-          v[c][e] = __float_as_uint(x);
-          mx = fmaxf(mx, x);
-        }
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[c][e]));
       }
       mx *= p.scale_log2;
       float alpha = 1.0f;
@@ -272,10 +276,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
             rs += p0 + p1;
             pk[e] = pack_half2(p0, p1);
           }
-          const int col8 = c * 4 + q4;        // 8-column piece index inside the BKV tile
-          const int cc = col8 >> 3, q = col8 & 7;
-          *reinterpret_cast<uint4*>(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4)) =
-              make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          const uint32_t col8 = c * 4 + q4;   // 8-column piece index inside the BKV tile
+          const uint32_t cc = col8 >> 3, q = col8 & 7u;
+          st_shared_v4(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
       }
       l_sum += rs;

@@ -14,6 +14,8 @@
 // A source selected per channel block.
 //
 // Algorithmic bytes per launch: 2*(M*K + N*K + M*N [+ M*N residual]) ; FLOPs 2*M*N*K.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 #include "../../include/mdk.h"
@@ -46,6 +48,7 @@ struct GemmParams {
   int out_trans[3];
   int trans_rows;
   long long trans_ld;
+  int dbg;  // MDK_GEMM_DEBUG bits (perf triage only): 1 = skip global stores, 2 = skip TMEM loads
 };
 
 template <int BN>
@@ -287,9 +290,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         for (int c = 0; c < BN; c += 32) {
           if (n0 + c >= p.N) break;  // warp-uniform
           uint32_t v[32];
-          tmem_ld_x32(t_acc + c, v);
-          tmem_wait_ld();
-          if (m >= 0) {
+          if (!(p.dbg & 2)) {
+            tmem_ld_x32(t_acc + c, v);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+          if (m >= 0 && !(p.dbg & 1)) {
             float o[32];
             const int nvalid = min(32, p.N - (n0 + c));
 #pragma unroll
@@ -442,6 +450,14 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
   p.seg_cols = a->seg_cols;
   p.trans_rows = a->trans_rows > 0 ? a->trans_rows : 1;
   p.trans_ld = a->trans_ld;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("MDK_GEMM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.dbg = dbg;
+  }
   int nseg = 1;
   const int ncols_out = a->geglu ? a->n / 2 : a->n;
   if (a->seg_cols > 0) {

@@ -58,25 +58,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
-#ifndef MDK_WAIT_LIMIT_NS
-#define MDK_WAIT_LIMIT_NS 4000000000ull
+// The watchdog uses the SM-local clock64 (cheap) and only starts after a burst of plain polls.
+#ifndef MDK_WAIT_LIMIT_CYCLES
+#define MDK_WAIT_LIMIT_CYCLES 8000000000ll  /* ~4 s at 2 GHz */
 #endif
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
-  return t;
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+#pragma unroll 1
+  for (int i = 0; i < 16; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0u && globaltimer_ns() - t0 > MDK_WAIT_LIMIT_NS) {
+    if ((++spins & 0xffu) == 0u && clock64() - t0 > MDK_WAIT_LIMIT_CYCLES) {
       printf("mdk: mbarrier wait timed out (block %d,%d thread %d bar 0x%x parity %u)\n",
              blockIdx.x, blockIdx.y, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
 }
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05 operand reads)

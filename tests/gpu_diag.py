@@ -384,6 +384,18 @@ def perf_gemm():
     return True
 
 
+def perf_gemm_small():
+    warm_gpu()
+    for (M, N, K) in [(294912, 320, 320), (294912, 2560, 320), (73728, 640, 640), (18432, 1280, 1280)]:
+        a = rnd(M, K).to(F16)
+        w = rnd(N, K, scale=K ** -0.5).to(F16)
+        out = torch.empty(M, N, dtype=F16, device=DEV)
+        ms = timeit_ms(lambda: ops.gemm(a, w, out=out))
+        print(f"perf[dbg={os.environ.get('MDK_GEMM_DEBUG', '0')}] gemm M={M} N={N} K={K}: {ms:.3f} ms  "
+              f"{2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s  {2.0 * (M * K + M * N) / ms / 1e6:.0f} GB/s", flush=True)
+    return True
+
+
 def perf_attn():
     warm_gpu()
     for (nimg, l, heads, d) in [(8, 9216, 8, 40), (32, 2304, 8, 80), (32, 576, 8, 160)]:
@@ -461,7 +473,7 @@ CHECKS = {
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
     "norms": check_norms, "temporal": check_temporal, "misc": check_misc, "attn": check_attn,
-    "perf_gemm": perf_gemm, "perf_attn": perf_attn, "ncu_gemm": ncu_gemm, "ncu_attn": ncu_attn,
+    "perf_gemm": perf_gemm, "perf_attn": perf_attn, "ncu_gemm": ncu_gemm, "perf_gemm_small": perf_gemm_small, "ncu_attn": ncu_attn,
 }
 
 if __name__ == "__main__":
