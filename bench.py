@@ -151,29 +151,42 @@ def build_model(cfg, dev):
     return model.to(device=dev, dtype=torch.float16).eval()
 
 
-def cpu_reference_sample(h, steps_cfg, reps, warm):
+def cpu_reference_sample(h, steps_cfg, reps, warm, budget_s=150.0):
     """The reference algorithm (fp32 oracle restating the reference modules) on the host cores.
-    Bounded sample: ONE frame (both CFG branches = 2 images) of one UNet forward at the config's
-    latent size; a clip step costs `frames` such samples, the clip `num_steps * frames`."""
+    Bounded sample: ONE frame (both CFG branches = 2 images) of one UNet forward.  The sample runs at
+    the config's latent size when (reps + warm) of them fit the time budget (predicted from a 32x32
+    calibration forward and the algorithmic FLOP ratio); otherwise at the largest of 64/48/32 that
+    fits, and the result is scaled by the algorithmic-FLOP ratio (stated in `sample`).  A clip step
+    costs `frames` such samples, the clip `num_steps * frames`."""
     from mikudance_b200 import synth
     from oracle import unet3d_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = synth.SD15_CONFIG
     sd = {k: v.float() for k, v in synth.synthetic_state_dict(cfg, seed=0).items()}
-    x, ctx = synth.synthetic_inputs(cfg, 2, 1, h, h, lctx=257)
-    banks = synth.synthetic_banks(cfg, 2, h, h)
-    times = []
-    with torch.no_grad():
-        for i in range(warm + reps):
+
+    def run(hs):
+        x, ctx = synth.synthetic_inputs(cfg, 2, 1, hs, hs, lctx=257)
+        banks = synth.synthetic_banks(cfg, 2, hs, hs)
+        with torch.no_grad():
             t0 = time.perf_counter()
             O.unet3d_forward(sd, cfg, x, 499, ctx, banks=banks, cfg_guidance=True)
-            dt = time.perf_counter() - t0
-            if i >= warm:
-                times.append(dt)
-    t = sum(times) / len(times)
-    fps = 1.0 / (steps_cfg * t)       # frames / (steps * frames * t)
-    return t, fps, cores
+            return time.perf_counter() - t0
+
+    fl = {hs: sum(per_image_flops(hs, 1).values()) for hs in {h, 64, 48, 32}}
+    run(32)
+    t32 = run(32)
+    hs = 32
+    for cand in sorted({h, 64, 48, 32}, reverse=True):
+        if cand <= h and (reps + warm) * t32 * fl[cand] / fl[32] <= budget_s:
+            hs = cand
+            break
+    times = [run(hs) for _ in range(warm + reps)][warm:]
+    t = sum(times) / len(times) * fl[h] / fl[hs]      # seconds for 2 images at the config's size
+    fps = 1.0 / (steps_cfg * t)                        # frames / (steps * frames * t)
+    note = (f"latent {hs}x{hs}" + ("" if hs == h else f" scaled to {h}x{h} by algorithmic FLOPs "
+                                                       f"x{fl[h] / fl[hs]:.2f}"))
+    return t, fps, cores, note
 
 
 def main():
@@ -199,14 +212,14 @@ def main():
         if rank != 0:
             return
         reps = max(1, args.steps)
-        t, fps, cores = cpu_reference_sample(h, num_steps, reps, max(0, min(args.warmup, 1)))
+        t, fps, cores, note = cpu_reference_sample(h, num_steps, reps, max(0, min(args.warmup, 1)))
         line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
                     warmup=args.warmup, ms_per_step=t * F_ * 1e3, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="f32", data="synthetic", impl="reference", config=workload,
                     cpu_baseline=dict(value=fps, unit="frames/s", cores=cores, kind="port",
                                       sample=f"1 of {F_} frames (2 CFG images) of one UNet forward per timed "
-                                             f"step, fp32 oracle of the reference modules; clip time "
-                                             f"extrapolated x{F_} frames x{num_steps} steps"),
+                                             f"step ({note}), fp32 oracle of the reference modules; clip "
+                                             f"time extrapolated x{F_} frames x{num_steps} steps"),
                     e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
@@ -313,11 +326,11 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        t, fps, cores = cpu_reference_sample(h, num_steps, 1, 0)
+        t, fps, cores, note = cpu_reference_sample(h, num_steps, 1, 0, budget_s=40.0)
         cpu = dict(value=fps, unit="frames/s", cores=cores, kind="port",
                    sample=f"1 of {F_} frames (2 CFG images) of one config-{args.config} UNet forward "
-                          f"({t:.1f} s), fp32 oracle restating the reference modules; extrapolated "
-                          f"x{F_} frames x{num_steps} steps")
+                          f"({note}; {t:.1f} s), fp32 oracle restating the reference modules; "
+                          f"extrapolated x{F_} frames x{num_steps} steps")
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps,

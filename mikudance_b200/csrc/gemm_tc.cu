@@ -48,24 +48,59 @@ struct GemmParams {
   int out_trans[3];
   int trans_rows;
   long long trans_ld;
-  int dbg;  // MDK_GEMM_DEBUG bits (perf triage only): 1 = skip global stores, 2 = skip TMEM loads
+  int dbg;  // MDK_GEMM_DEBUG bit 1 (perf triage only): skip the global stores of the epilogue
 };
 
 template <int BN>
 struct GemmCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 160 ? 5 : 6);
+  static constexpr int EPI_STAGING = 4 * 32 * 64;  // per epilogue warp: 32 rows x 32 fp16
   static constexpr int TMEM_COLS = (2 * BN <= 32)    ? 32
                                    : (2 * BN <= 64)  ? 64
                                    : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256
                                                      : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + EPI_STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// Write a warp's 32 rows x 32 fp16 columns: every lane holds one row (o[32]).  Direct per-lane
+// stores would be 16-byte pieces scattered over 32 rows (partial-sector writes: measured 5x slower
+// than the rest of the kernel), so the sub-tile is transposed through a 2 KB warp-private staging
+// buffer (XOR-swizzled, conflict free) and written as full 64-byte row segments: one store
+// instruction covers 8 rows x 64 B.
+__device__ __forceinline__ void store_chunk_coalesced(const float (&o)[32], uint32_t stage_addr,
+                                                      int lane, int m_mine, __half* obase,
+                                                      long long ldo, int col0, int nvalid) {
+  const uint32_t my = stage_addr + static_cast<uint32_t>(lane) * 64u;
+  const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+#pragma unroll
+  for (uint32_t q = 0; q < 4; ++q) {
+    st_shared_v4(my + ((q ^ sw) << 4), pack_half2(o[q * 8 + 0], o[q * 8 + 1]),
+                 pack_half2(o[q * 8 + 2], o[q * 8 + 3]), pack_half2(o[q * 8 + 4], o[q * 8 + 5]),
+                 pack_half2(o[q * 8 + 6], o[q * 8 + 7]));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = i * 32 + lane;
+    const int row = t >> 2;
+    const uint32_t q = static_cast<uint32_t>(t & 3);
+    const int m_r = __shfl_sync(0xffffffffu, m_mine, row);
+    uint4 val;
+    ld_shared_v4(stage_addr + static_cast<uint32_t>(row) * 64u +
+                     ((q ^ static_cast<uint32_t>((row >> 1) & 3)) << 4),
+                 val);
+    if (m_r >= 0 && static_cast<int>(q) * 8 < nvalid)
+      *reinterpret_cast<uint4*>(obase + static_cast<long long>(m_r) * ldo + col0 + q * 8) = val;
+  }
+  __syncwarp();
 }
 
 template <int BN>
@@ -79,7 +114,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_STAGING);
   uint64_t* full_bar = bars;                     // [STAGES]
   uint64_t* empty_bar = bars + STAGES;           // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]
@@ -200,6 +236,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     // ======================= epilogue warps =======================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row_in_tile = quarter * 32 + lane;
+    const uint32_t stage_addr = smem_u32(smem_epi) + static_cast<uint32_t>(quarter) * 2048u;
     uint32_t acc_phase[2] = {0, 0};
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -233,6 +270,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       const uint32_t t_acc =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
+      const int m32 = static_cast<int>(m);  // M fits in int32 (checked on the host)
       if (p.geglu) {
         // tile columns [0, BN/2) are values, [BN/2, BN) the matching gates
         constexpr int HALF = BN / 2;
@@ -243,43 +281,35 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           tmem_ld_x32(t_acc + c, vh);
           tmem_ld_x32(t_acc + HALF + c, vg);
           tmem_wait_ld();
-          if (m >= 0) {
-            float o[32];
+          float o[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float hval = __uint_as_float(vh[j]);
-              float gval = __uint_as_float(vg[j]);
-              if (p.bias) {
-                hval += __ldg(p.bias + n0 + c + j);
-                gval += __ldg(p.bias + n0 + HALF + c + j);
-              }
-              o[j] = hval * gelu_erf(gval);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
+            if (p.bias) {
+              bh = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + j4);
+              bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + HALF + c) + j4);
             }
-            __half* dst = p.out[0] + m * p.ldo[0] + ocol0 + c;
-            if (p.residual) {
-              const __half* rsrc = p.residual + m * p.ldr + ocol0 + c;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 rv = *reinterpret_cast<const uint4*>(rsrc + q * 8);
-                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = __half22float2(rh[e]);
-                  o[q * 8 + 2 * e] += f.x;
-                  o[q * 8 + 2 * e + 1] += f.y;
-                }
-              }
-            }
+            o[j4 * 4 + 0] = (__uint_as_float(vh[j4 * 4 + 0]) + bh.x) * gelu_erf(__uint_as_float(vg[j4 * 4 + 0]) + bg.x);
+            o[j4 * 4 + 1] = (__uint_as_float(vh[j4 * 4 + 1]) + bh.y) * gelu_erf(__uint_as_float(vg[j4 * 4 + 1]) + bg.y);
+            o[j4 * 4 + 2] = (__uint_as_float(vh[j4 * 4 + 2]) + bh.z) * gelu_erf(__uint_as_float(vg[j4 * 4 + 2]) + bg.z);
+            o[j4 * 4 + 3] = (__uint_as_float(vh[j4 * 4 + 3]) + bh.w) * gelu_erf(__uint_as_float(vg[j4 * 4 + 3]) + bg.w);
+          }
+          if (p.residual && m >= 0) {
+            const __half* rsrc = p.residual + m * p.ldr + ocol0 + c;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint4 pk;
-              pk.x = pack_half2(o[q * 8 + 0], o[q * 8 + 1]);
-              pk.y = pack_half2(o[q * 8 + 2], o[q * 8 + 3]);
-              pk.z = pack_half2(o[q * 8 + 4], o[q * 8 + 5]);
-              pk.w = pack_half2(o[q * 8 + 6], o[q * 8 + 7]);
-              *reinterpret_cast<uint4*>(dst + q * 8) = pk;
+              uint4 rv = *reinterpret_cast<const uint4*>(rsrc + q * 8);
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __half22float2(rh[e]);
+                o[q * 8 + 2 * e] += f.x;
+                o[q * 8 + 2 * e + 1] += f.y;
+              }
             }
           }
+          if (!(p.dbg & 1))
+            store_chunk_coalesced(o, stage_addr, lane, m32, p.out[0], p.ldo[0], ocol0 + c, 32);
         }
       } else {
         const int seg = (p.seg_cols > 0) ? (n0 / p.seg_cols) : 0;
@@ -290,63 +320,52 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         for (int c = 0; c < BN; c += 32) {
           if (n0 + c >= p.N) break;  // warp-uniform
           uint32_t v[32];
-          if (!(p.dbg & 2)) {
-            tmem_ld_x32(t_acc + c, v);
-            tmem_wait_ld();
-          } else {
+          tmem_ld_x32(t_acc + c, v);
+          tmem_wait_ld();
+          const int nvalid = min(32, p.N - (n0 + c));   // multiple of 8
+          float o[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j4 * 4 < nvalid) {
+              if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + j4);
+              if (rb) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(rb + n0 + c) + j4);
+                b.x += r.x; b.y += r.y; b.z += r.z; b.w += r.w;
+              }
+            }
+            o[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b.x;
+            o[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b.y;
+            o[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b.z;
+            o[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b.w;
           }
-          if (m >= 0 && !(p.dbg & 1)) {
-            float o[32];
-            const int nvalid = min(32, p.N - (n0 + c));
+          if (p.residual && m >= 0) {
+            const __half* rsrc = p.residual + m * p.ldr + n0 + c;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < nvalid) {
+                uint4 rv = *reinterpret_cast<const uint4*>(rsrc + q * 8);
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __half22float2(rh[e]);
+                  o[q * 8 + 2 * e] += f.x;
+                  o[q * 8 + 2 * e + 1] += f.y;
+                }
+              }
+            }
+          }
+          if (p.dbg & 1) continue;
+          if (!trans) {
+            store_chunk_coalesced(o, stage_addr, lane, m32, obase, ldo, seg_col0 + c, nvalid);
+          } else if (m >= 0) {
+            // per-image transposed store: lanes hold consecutive rows -> 64-byte runs per column
+            const long long img = m / p.trans_rows;
+            const long long l = m % p.trans_rows;
+            __half* dst = obase + (img * p.seg_cols + seg_col0 + c) * p.trans_ld + l;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(v[j]);
-              if (j < nvalid) {
-                if (p.bias) x += __ldg(p.bias + n0 + c + j);
-                if (rb) x += __ldg(rb + n0 + c + j);
-              }
-              o[j] = x;
-            }
-            if (p.residual) {
-              const __half* rsrc = p.residual + m * p.ldr + n0 + c;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (q * 8 < nvalid) {
-                  uint4 rv = *reinterpret_cast<const uint4*>(rsrc + q * 8);
-                  const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    float2 f = __half22float2(rh[e]);
-                    o[q * 8 + 2 * e] += f.x;
-                    o[q * 8 + 2 * e + 1] += f.y;
-                  }
-                }
-              }
-            }
-            if (!trans) {
-              __half* dst = obase + m * ldo + seg_col0 + c;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (q * 8 < nvalid) {
-                  uint4 pk;
-                  pk.x = pack_half2(o[q * 8 + 0], o[q * 8 + 1]);
-                  pk.y = pack_half2(o[q * 8 + 2], o[q * 8 + 3]);
-                  pk.z = pack_half2(o[q * 8 + 4], o[q * 8 + 5]);
-                  pk.w = pack_half2(o[q * 8 + 6], o[q * 8 + 7]);
-                  *reinterpret_cast<uint4*>(dst + q * 8) = pk;
-                }
-              }
-            } else {
-              // per-image transposed store: lanes hold consecutive rows -> 64-byte runs per column
-              const long long img = m / p.trans_rows;
-              const long long l = m % p.trans_rows;
-              __half* dst = obase + (img * p.seg_cols + seg_col0 + c) * p.trans_ld + l;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j < nvalid) dst[static_cast<long long>(j) * p.trans_ld] = __float2half_rn(o[j]);
-              }
+              if (j < nvalid) dst[static_cast<long long>(j) * p.trans_ld] = __float2half_rn(o[j]);
             }
           }
         }
@@ -480,6 +499,9 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
                     "mdk_gemm_f16: out[%d] must be 16-byte aligned with ldo %% 8 == 0", s);
     }
   }
+  MDK_REQUIRE((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->row_bias) & 15) == 0,
+              "mdk_gemm_f16: bias / row_bias must be 16-byte aligned");
   if (a->residual)
     MDK_REQUIRE(a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0,
                 "mdk_gemm_f16: residual must be 16-byte aligned with ldr %% 8 == 0");

@@ -63,13 +63,28 @@ __global__ void gn_stats_kernel(const GnParams p) {
     float s[8], q[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
-    for (int px = pbeg + threadIdx.y; px < pend; px += blockDim.y) {
-      float v[8];
-      load8(src + (static_cast<long long>(img) * p.hw + px) * cs + coff, v);
+    const int stepy = blockDim.y;
+    for (int px = pbeg + threadIdx.y; px < pend; px += 4 * stepy) {
+      // four independent 16-byte loads in flight per thread
+      uint4 raw[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        s[e] += v[e];
-        q[e] += v[e] * v[e];
+      for (int u = 0; u < 4; ++u) {
+        const int pp = px + u * stepy;
+        raw[u] = (pp < pend) ? *reinterpret_cast<const uint4*>(
+                                   src + (static_cast<long long>(img) * p.hw + pp) * cs + coff)
+                             : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __half2* h = reinterpret_cast<const __half2*>(&raw[u]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          s[2 * e] += f.x;
+          q[2 * e] += f.x * f.x;
+          s[2 * e + 1] += f.y;
+          q[2 * e + 1] += f.y * f.y;
+        }
       }
     }
     // combine the (at most a few) groups this vector touches
@@ -126,22 +141,41 @@ __global__ void gn_apply_kernel(const GnParams p) {
   }
   const int pbeg = blockIdx.x * p.pix_per_cta;
   const int pend = min(p.hw, pbeg + p.pix_per_cta);
-  for (int px = pbeg + threadIdx.y; px < pend; px += blockDim.y) {
-    float v[8];
-    const long long pix = static_cast<long long>(img) * p.hw + px;
-    load8(src + pix * cs + coff, v);
+  const int stepy = blockDim.y;
+  for (int px = pbeg + threadIdx.y; px < pend; px += 4 * stepy) {
+    uint4 raw[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float y = v[e] * scale[e] + shift[e];
-      if (p.silu) y = y / (1.0f + __expf(-y));
-      v[e] = y;
+    for (int u = 0; u < 4; ++u) {
+      const int pp = px + u * stepy;
+      if (pp < pend)
+        raw[u] = *reinterpret_cast<const uint4*>(src + (static_cast<long long>(img) * p.hw + pp) * cs + coff);
     }
-    store8(p.out + pix * p.C + ch, v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pp = px + u * stepy;
+      if (pp < pend) {
+        const __half2* h = reinterpret_cast<const __half2*>(&raw[u]);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          v[2 * e] = f.x;
+          v[2 * e + 1] = f.y;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float y = v[e] * scale[e] + shift[e];
+          if (p.silu) y = y / (1.0f + __expf(-y));
+          v[e] = y;
+        }
+        store8(p.out + (static_cast<long long>(img) * p.hw + pp) * p.C + ch, v);
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, row held in registers (C <= 8*32*LN_MAXV), two-pass variance.
+// LayerNorm: one warp per R rows, rows held in registers (C <= 8*32*LN_MAXV), two-pass variance.
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_MAXV = 6;  // C <= 1536
 
@@ -158,65 +192,104 @@ struct LnParams {
   long long add_row0;
 };
 
+// NV = 16-byte vectors per lane per row, R = rows a warp processes together (R*NV loads in flight
+// per lane: the kernel is latency-bound otherwise).
+template <int NV, int R>
 __global__ void layernorm_kernel(const LnParams p) {
   const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int V = p.c >> 3;
-  const long long row0 = static_cast<long long>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5);
-  const long long row_stride = static_cast<long long>(gridDim.x) * warps_per_cta;
-  for (long long row = row0; row < p.rows; row += row_stride) {
-    float v[LN_MAXV][8];
-    float sum = 0.f;
-    const __half* src = p.x + row * p.c;
+  const long long w0 = static_cast<long long>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5);
+  const long long wstride = static_cast<long long>(gridDim.x) * warps_per_cta;
+  const float inv_c = 1.0f / static_cast<float>(p.c);
+  for (long long rb = w0 * R; rb < p.rows; rb += wstride * R) {
+    uint4 raw[R][NV];
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-      const int cv = lane + i * 32;
-      if (cv < V) {
-        load8(src + cv * 8, v[i]);
+    for (int r = 0; r < R; ++r) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sum += v[i][e];
+      for (int i = 0; i < NV; ++i) {
+        const int cv = lane + i * 32;
+        raw[r][i] = (rb + r < p.rows && cv < V)
+                        ? *reinterpret_cast<const uint4*>(p.x + (rb + r) * p.c + cv * 8)
+                        : make_uint4(0, 0, 0, 0);
       }
     }
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / static_cast<float>(p.c);
-    float sq = 0.f;
+    for (int r = 0; r < R; ++r) {
+      float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-      const int cv = lane + i * 32;
-      if (cv < V) {
+      for (int i = 0; i < NV; ++i) {
+        const __half2* h = reinterpret_cast<const __half2*>(&raw[r][i]);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float d = v[i][e] - mean;
-          sq += d * d;
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          sum += f.x + f.y;
         }
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      mean[r] = sum * inv_c;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (lane + i * 32 < V) {
+          const __half2* h = reinterpret_cast<const __half2*>(&raw[r][i]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            const float d0 = f.x - mean[r], d1 = f.y - mean[r];
+            sq += d0 * d0 + d1 * d1;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      rstd[r] = rsqrtf(sq * inv_c + p.eps);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq / static_cast<float>(p.c) + p.eps);
-    const bool do_add = p.add != nullptr && row >= p.add_row0;
-#pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int cv = lane + i * 32;
       if (cv < V) {
-        float gm[8], bt[8], y[8];
+        float gm[8], bt[8];
         load8(p.gamma + cv * 8, gm);
         load8(p.beta + cv * 8, bt);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = (v[i][e] - mean) * rstd * gm[e] + bt[e];
-        store8(p.out + row * p.c + cv * 8, y);
-        if (do_add) {
-          float ad[8];
-          const long long r2 = row - p.add_row0;
-          load8(p.add + r2 * p.c + cv * 8, ad);
+        for (int r = 0; r < R; ++r) {
+          const long long row = rb + r;
+          if (row < p.rows) {
+            const __half2* h = reinterpret_cast<const __half2*>(&raw[r][i]);
+            float y[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) y[e] += ad[e];
-          store8(p.out2 + r2 * p.c + cv * 8, y);
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(h[e]);
+              y[2 * e] = (f.x - mean[r]) * rstd[r] * gm[2 * e] + bt[2 * e];
+              y[2 * e + 1] = (f.y - mean[r]) * rstd[r] * gm[2 * e + 1] + bt[2 * e + 1];
+            }
+            store8(p.out + row * p.c + cv * 8, y);
+            if (p.add != nullptr && row >= p.add_row0) {
+              float ad[8];
+              const long long r2 = row - p.add_row0;
+              load8(p.add + r2 * p.c + cv * 8, ad);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] += ad[e];
+              store8(p.out2 + r2 * p.c + cv * 8, y);
+            }
+          }
         }
       }
     }
   }
+}
+
+template <int NV, int R>
+static void launch_ln(const LnParams& p, int num_sms, cudaStream_t stream) {
+  const int warps = 8;
+  long long groups = (p.rows + R - 1) / R;
+  long long ctas = (groups + warps - 1) / warps;
+  const long long cap = static_cast<long long>(num_sms) * 8;
+  if (ctas > cap) ctas = cap;
+  layernorm_kernel<NV, R><<<static_cast<unsigned>(ctas), warps * 32, 0, stream>>>(p);
 }
 
 }  // namespace mdk
@@ -294,11 +367,14 @@ extern "C" int mdk_layernorm_f16(mdk_ctx* ctx, const mdk_ln_args* a, void* strea
   p.add = static_cast<const __half*>(a->add);
   p.out2 = static_cast<__half*>(a->out2);
   p.add_row0 = a->add_row0;
-  const int warps = 8;
-  long long ctas = (a->rows + warps - 1) / warps;
-  const long long cap = static_cast<long long>(ctx->num_sms) * 16;
-  if (ctas > cap) ctas = cap;
-  layernorm_kernel<<<static_cast<unsigned>(ctas), warps * 32, 0, stream>>>(p);
+  switch ((a->c / 8 + 31) / 32) {
+    case 1: launch_ln<1, 4>(p, ctx->num_sms, stream); break;
+    case 2: launch_ln<2, 3>(p, ctx->num_sms, stream); break;
+    case 3: launch_ln<3, 2>(p, ctx->num_sms, stream); break;
+    case 4: launch_ln<4, 1>(p, ctx->num_sms, stream); break;
+    case 5: launch_ln<5, 1>(p, ctx->num_sms, stream); break;
+    default: launch_ln<6, 1>(p, ctx->num_sms, stream); break;
+  }
   count_launch();
   MDK_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -165,6 +165,147 @@ __global__ void temporal_attn_kernel(const TattnParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled variant for the single-GPU layout (fused q|k|v rows [M, 3C], f_q == f_kv): a CTA owns PG
+// consecutive pixels of one batch entry, stages their f x 3C rows with fully coalesced 16-byte loads
+// (consecutive pixels of one frame are contiguous in memory), computes every (pixel, head) problem
+// from shared memory, overwrites the Q slots with O and writes the outputs back coalesced.
+// ------------------------------------------------------------------------------------------------
+struct TattnTileParams {
+  const __half* qkv;
+  const float* pe_q;
+  __half* out;
+  long long ld, out_ld;
+  int nb, f, npix, heads, d, C;
+  int pg;        // pixels per CTA
+  int rs;        // smem row stride in halves (3C + 8)
+  int qpw;
+  float scale_log2;
+};
+
+template <int FKV_MAX>
+__global__ void temporal_attn_tile_kernel(const TattnTileParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __half* sm = reinterpret_cast<__half*>(smem_raw);
+  const int groups_per_b = (p.npix + p.pg - 1) / p.pg;
+  const int b = blockIdx.x / groups_per_b;
+  const int px0 = (blockIdx.x % groups_per_b) * p.pg;
+  const int npx = min(p.pg, p.npix - px0);
+  const int rowv = (3 * p.C) >> 3;  // 16-byte vectors per row
+  // ---- coalesced load: for each frame the npx pixel rows are one contiguous run ----
+  for (int j = 0; j < p.f; ++j) {
+    const __half* src = p.qkv + ((static_cast<long long>(b) * p.f + j) * p.npix + px0) * p.ld;
+    for (int i = threadIdx.x; i < npx * rowv; i += blockDim.x) {
+      const int px = i / rowv, v = i % rowv;
+      *reinterpret_cast<uint4*>(sm + (static_cast<long long>(px) * p.f + j) * p.rs + v * 8) =
+          *reinterpret_cast<const uint4*>(src + static_cast<long long>(px) * p.ld + v * 8);
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int ppw = 32 / p.qpw;
+  const int nprob = npx * p.heads;
+  const int dv = p.d >> 3;
+  for (int g = warp; g * ppw < nprob; g += warps) {
+    const int pr = g * ppw + lane / p.qpw;
+    const int i = lane % p.qpw;
+    if (pr < nprob && i < p.f) {
+      const int px = pr / p.heads, h = pr % p.heads;
+      __half* base = sm + static_cast<long long>(px) * p.f * p.rs;
+      __half* qrow = base + static_cast<long long>(i) * p.rs + h * p.d;
+      const __half* k0 = base + p.C + h * p.d;
+      const __half* v0 = base + 2 * p.C + h * p.d;
+      const float* peptr = p.pe_q ? p.pe_q + static_cast<long long>(i) * p.C + h * p.d : nullptr;
+      float s[FKV_MAX];
+#pragma unroll
+      for (int j = 0; j < FKV_MAX; ++j) s[j] = 0.f;
+      for (int v = 0; v < dv; ++v) {
+        float qv[8];
+        {
+          uint4 raw = *reinterpret_cast<const uint4*>(qrow + v * 8);
+          const __half2* hq = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f2 = __half22float2(hq[e]);
+            qv[2 * e] = f2.x;
+            qv[2 * e + 1] = f2.y;
+          }
+          if (peptr) {
+            const float4 a = *reinterpret_cast<const float4*>(peptr + v * 8);
+            const float4 c = *reinterpret_cast<const float4*>(peptr + v * 8 + 4);
+            qv[0] += a.x; qv[1] += a.y; qv[2] += a.z; qv[3] += a.w;
+            qv[4] += c.x; qv[5] += c.y; qv[6] += c.z; qv[7] += c.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < FKV_MAX; ++j) {
+          if (j < p.f) {
+            uint4 raw = *reinterpret_cast<const uint4*>(k0 + static_cast<long long>(j) * p.rs + v * 8);
+            const __half2* hk = reinterpret_cast<const __half2*>(&raw);
+            float a = s[j];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f2 = __half22float2(hk[e]);
+              a = fmaf(qv[2 * e], f2.x, a);
+              a = fmaf(qv[2 * e + 1], f2.y, a);
+            }
+            s[j] = a;
+          }
+        }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < FKV_MAX; ++j)
+        if (j < p.f) mx = fmaxf(mx, s[j]);
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < FKV_MAX; ++j) {
+        if (j < p.f) {
+          s[j] = exp2f((s[j] - mx) * p.scale_log2);
+          l += s[j];
+        }
+      }
+      const float inv = 1.0f / l;
+      for (int v = 0; v < dv; ++v) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < FKV_MAX; ++j) {
+          if (j < p.f) {
+            uint4 raw = *reinterpret_cast<const uint4*>(v0 + static_cast<long long>(j) * p.rs + v * 8);
+            const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f2 = __half22float2(hv[e]);
+              o[2 * e] = fmaf(s[j], f2.x, o[2 * e]);
+              o[2 * e + 1] = fmaf(s[j], f2.y, o[2 * e + 1]);
+            }
+          }
+        }
+        uint4 pk;
+        pk.x = pack_half2(o[0] * inv, o[1] * inv);
+        pk.y = pack_half2(o[2] * inv, o[3] * inv);
+        pk.z = pack_half2(o[4] * inv, o[5] * inv);
+        pk.w = pack_half2(o[6] * inv, o[7] * inv);
+        // the query slot of this (frame, head) is dead: reuse it for the output row
+        *reinterpret_cast<uint4*>(qrow + v * 8) = pk;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- coalesced store of the O rows (first C columns of every staged row) ----
+  const int outv = p.C >> 3;
+  for (int j = 0; j < p.f; ++j) {
+    __half* dst = p.out + ((static_cast<long long>(b) * p.f + j) * p.npix + px0) * p.out_ld;
+    for (int i = threadIdx.x; i < npx * outv; i += blockDim.x) {
+      const int px = i / outv, v = i % outv;
+      *reinterpret_cast<uint4*>(dst + static_cast<long long>(px) * p.out_ld + v * 8) =
+          *reinterpret_cast<const uint4*>(sm + (static_cast<long long>(px) * p.f + j) * p.rs + v * 8);
+    }
+  }
+}
+
 }  // namespace mdk
 
 extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void* stream_) {
@@ -180,6 +321,57 @@ extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void
   MDK_REQUIRE(a->q_ld % 8 == 0 && a->kv_ld % 8 == 0 && a->out_ld % 8 == 0 && a->q_off % 8 == 0 &&
                   a->k_off % 8 == 0 && a->v_off % 8 == 0,
               "mdk_temporal_attn_f16: leading dimensions / offsets must be multiples of 8");
+  // ---- tiled fast path: fused q|k|v rows, all frames local ----
+  {
+    const int C = a->heads * a->d;
+    const bool fused = a->q == a->kv && a->q_off == 0 && a->k_off == C && a->v_off == 2 * C &&
+                       a->q_ld == a->kv_ld && a->q_ld >= 3 * C && a->f_q == a->f_kv &&
+                       f_kv_rank == a->f_kv && a->f_q_offset == 0;
+    const int rs = 3 * C + 8;
+    const size_t per_px = static_cast<size_t>(a->f_q) * rs * sizeof(__half);
+    if (fused && per_px <= 200 * 1024) {
+      TattnTileParams t;
+      t.qkv = static_cast<const __half*>(a->q);
+      t.pe_q = a->pe_q;
+      t.out = static_cast<__half*>(a->out);
+      t.ld = a->q_ld;
+      t.out_ld = a->out_ld;
+      t.nb = a->nb;
+      t.f = a->f_q;
+      t.npix = a->npix;
+      t.heads = a->heads;
+      t.d = a->d;
+      t.C = C;
+      t.rs = rs;
+      int qpw = 1;
+      while (qpw < a->f_q) qpw *= 2;
+      t.qpw = qpw;
+      t.scale_log2 = a->scale * 1.4426950408889634f;
+      int pg = static_cast<int>((96 * 1024) / per_px);   // two CTAs per SM when possible
+      if (pg < 1) pg = 1;
+      if (pg > a->npix) pg = a->npix;
+      if (pg > 8) pg = 8;
+      t.pg = pg;
+      const size_t smem = per_px * pg;
+      const int groups = (a->npix + pg - 1) / pg;
+      static bool tile_attr = false;
+      if (!tile_attr) {
+        MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_tile_kernel<16>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_tile_kernel<32>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        tile_attr = true;
+      }
+      const unsigned grid = static_cast<unsigned>(a->nb) * groups;
+      if (a->f_q <= 16)
+        temporal_attn_tile_kernel<16><<<grid, 256, smem, stream>>>(t);
+      else
+        temporal_attn_tile_kernel<32><<<grid, 256, smem, stream>>>(t);
+      count_launch();
+      MDK_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   TattnParams p;
   p.q = static_cast<const __half*>(a->q);
   p.kv = static_cast<const __half*>(a->kv);

@@ -1,13 +1,12 @@
 #!/bin/bash
-# One GPU call: attention v2 check + perf, GEMM epilogue triage, ncu capture of the GEMM, quick bench.
+# One GPU call: full GPU test suite, microbenchmarks, bench.py, ncu launch list + attention capture.
 mkdir -p gpurun_out
 make -j8 >/dev/null 2>&1 || echo "MAKE FAILED"
 export PYTHONUNBUFFERED=1
-( timeout 300 python tests/gpu_diag.py attn perf_attn 2>&1 | tail -30 ) | tee gpurun_out/attn_v2.log
-for f in 0 1 3; do
-  ( MDK_GEMM_DEBUG=$f timeout 200 python tests/gpu_diag.py perf_gemm_small 2>&1 | grep perf ) | tee -a gpurun_out/gemm_triage.log
-done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 2 -c 2 -o gpurun_out/prof_gemm python tests/gpu_diag.py ncu_gemm > gpurun_out/ncu_gemm.log 2>&1; tail -3 gpurun_out/ncu_gemm.log
-( timeout 900 python bench.py --steps 5 --warmup 3 --skip-cpu-baseline 2> gpurun_out/bench_stderr.log | tee gpurun_out/bench_v2.json ) | cut -c1-600
+( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) | tee gpurun_out/pytest_gpu.log
+( timeout 300 python tests/gpu_diag.py perf_gemm_small perf_gemm perf_attn 2>&1 | grep -E "perf|==" ) | tee gpurun_out/perf_micro.log
+( timeout 900 python bench.py --steps 10 --warmup 3 2> gpurun_out/bench_stderr.log | tee gpurun_out/bench.json ) | cut -c1-700
 tail -5 gpurun_out/bench_stderr.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-graph --skip-profile --skip-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; tail -2 gpurun_out/bench_under_ncu.log | cut -c1-300
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 1 -c 1 -o gpurun_out/prof_attn_v2 python tests/gpu_diag.py ncu_attn > gpurun_out/ncu_attn.log 2>&1; tail -2 gpurun_out/ncu_attn.log
 ls -la gpurun_out
