@@ -147,7 +147,8 @@ int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* args, void* stream
  *   src/models/resnet.py:20-28,220-221,231-236; src/models/transformer_3d.py:60-62,130;
  *   src/models/motion_module.py:121-123,160; src/models/unet_3d_mix.py:591-592.
  * Input is one or two channel-concatenated NHWC sources [nimg, hw, c_i].
- * mdk_groupnorm_f16: stats (fp32 partials, fp64 finalize) + apply (+SiLU) -> out [nimg, hw, c0+c1].
+ * mdk_groupnorm_f16: stats (fp32 partials per CTA, fixed-order fp64 combine: bitwise deterministic, no
+ *   atomics) + apply (+SiLU) -> out [nimg, hw, c0+c1].
  * ws: workspace of mdk_groupnorm_ws_bytes(nimg, groups) bytes.
  */
 typedef struct {

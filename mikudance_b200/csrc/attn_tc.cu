@@ -23,6 +23,18 @@ constexpr int ATT_BQ = 128;
 constexpr int ATT_THREADS = 192;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
+// exp2 on the FMA/ALU pipes (Cody-Waite reduction + degree-3 minimax polynomial, max relative error
+// 7.5e-5 — below the fp16 rounding P gets anyway).  The d=40 self-attention is bound by the MUFU
+// pipe (one ex2 per score, 16/clk/SM), so a quarter of the exponentials is moved here.
+__device__ __forceinline__ float ex2_poly3(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float n = t - 12582912.0f;
+  const float f = x - n;            // [-0.5, 0.5]
+  const float pl = fmaf(fmaf(fmaf(0.05517165f, f, 0.24261113f), f, 0.69326097f), f, 0.99992806f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
+
 struct AttnParams {
   CUtensorMap tmQ, tmK, tmV;
   __half* out;
@@ -271,8 +283,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           for (int e = 0; e < 4; ++e) {
             const float p0 =
                 ex2_approx(fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e]), p.scale_log2, -m_used));
-            const float p1 =
-                ex2_approx(fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used));
+            const float x1 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used);
+            const float p1 = (e & 1) ? ex2_poly3(x1) : ex2_approx(x1);   // 2 of every 8 on the FMA pipe
             rs += p0 + p1;
             pk[e] = pack_half2(p0, p1);
           }

@@ -5,9 +5,10 @@
 // One persistent CTA per SM, 192 threads:
 //   warp 0   : TMA producer  (A tile 128 x 64 and B tile BN x 64 per stage, 128B-swizzled)
 //   warp 1   : MMA issuer    (one elected lane issues tcgen05.mma 128 x BN x 16, 4 per stage)
-//   warps 2-5: epilogue      (tcgen05.ld of the accumulator, fused bias / row-bias / GEGLU /
-//                             residual, fp16 stores) — overlaps the next tile's main loop through
-//                             two TMEM accumulator buffers.
+//   warps 2-9: epilogue      (tcgen05.ld of the accumulator, fused bias / row-bias / GEGLU /
+//                             residual, fp16 stores through a swizzled smem transpose) — two warps
+//                             per TMEM lane quarter, interleaved over the 32-column chunks; overlaps
+//                             the next tile's main loop through two TMEM accumulator buffers.
 // Convolution mode walks K as (tap, channel block): for every tap the A tile is one 4-D TMA box
 // [bn images, bh rows, bw cols, 64 ch] shifted by (kh-1, kw-1); out-of-bounds pixels are
 // zero-filled by TMA, which is exactly the conv's zero padding.  The skip concat is a second
@@ -25,7 +26,8 @@ namespace mdk {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int EPI_WARPS = 8;
 
 struct GemmParams {
   CUtensorMap tmA0, tmA1, tmB;
@@ -56,7 +58,7 @@ struct GemmCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 160 ? 5 : 6);
-  static constexpr int EPI_STAGING = 4 * 32 * 64;  // per epilogue warp: 32 rows x 32 fp16
+  static constexpr int EPI_STAGING = EPI_WARPS * 32 * 64;  // per epilogue warp: 32 rows x 32 fp16
   static constexpr int TMEM_COLS = (2 * BN <= 32)    ? 32
                                    : (2 * BN <= 64)  ? 64
                                    : (2 * BN <= 128) ? 128
@@ -137,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -234,9 +236,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     }
   } else {
     // ======================= epilogue warps =======================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int cgroup = (warp - 2) >> 2;     // 0/1: which half of the 32-column chunks this warp takes
     const int row_in_tile = quarter * 32 + lane;
-    const uint32_t stage_addr = smem_u32(smem_epi) + static_cast<uint32_t>(quarter) * 2048u;
+    const uint32_t stage_addr = smem_u32(smem_epi) + static_cast<uint32_t>(warp - 2) * 2048u;
     uint32_t acc_phase[2] = {0, 0};
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -275,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         // tile columns [0, BN/2) are values, [BN/2, BN) the matching gates
         constexpr int HALF = BN / 2;
         const int ocol0 = n_tile * HALF;
-        for (int c = 0; c < HALF; c += 32) {
+        for (int c = cgroup * 32; c < HALF; c += 64) {
           if (n0 + c >= p.N) break;
           uint32_t vh[32], vg[32];
           tmem_ld_x32(t_acc + c, vh);
@@ -317,11 +320,17 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         __half* obase = p.out[seg];
         const long long ldo = p.ldo[seg];
         const bool trans = p.out_trans[seg] != 0;
-        for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        int c = cgroup * 32;
+        if (n0 + c < p.N && c < BN) tmem_ld_x32(t_acc + c, v);
+        for (; c < BN; c += 64) {
           if (n0 + c >= p.N) break;  // warp-uniform
-          uint32_t v[32];
-          tmem_ld_x32(t_acc + c, v);
           tmem_wait_ld();
+          float acc_f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc_f[j] = __uint_as_float(v[j]);
+          // prefetch this warp's next chunk while the current one is converted and stored
+          if (c + 64 < BN && n0 + c + 64 < p.N) tmem_ld_x32(t_acc + c + 64, v);
           const int nvalid = min(32, p.N - (n0 + c));   // multiple of 8
           float o[32];
 #pragma unroll
@@ -334,10 +343,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
                 b.x += r.x; b.y += r.y; b.z += r.z; b.w += r.w;
               }
             }
-            o[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b.x;
-            o[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b.y;
-            o[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b.z;
-            o[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b.w;
+            o[j4 * 4 + 0] = acc_f[j4 * 4 + 0] + b.x;
+            o[j4 * 4 + 1] = acc_f[j4 * 4 + 1] + b.y;
+            o[j4 * 4 + 2] = acc_f[j4 * 4 + 2] + b.z;
+            o[j4 * 4 + 3] = acc_f[j4 * 4 + 3] + b.w;
           }
           if (p.residual && m >= 0) {
             const __half* rsrc = p.residual + m * p.ldr + n0 + c;

@@ -9,6 +9,8 @@
 
 namespace mdk {
 
+constexpr int GN_MAX_CHUNKS = 64;
+
 struct GnParams {
   const __half* x0;
   const __half* x1;
@@ -19,8 +21,9 @@ struct GnParams {
   const __half* beta;
   int silu;
   __half* out;
-  double* ws;  // [nimg, groups, 2] sum, sumsq
+  float* ws;  // [nimg, GN_MAX_CHUNKS, groups, 2] per-CTA partial (sum, sumsq)
   int pix_per_cta;
+  int nchunks;
 };
 
 __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
@@ -44,14 +47,19 @@ __device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
 
 // blockDim = (vx, vy): thread x owns channel vector cv = threadIdx.x (8 channels), thread y strides
 // over the pixels of this CTA's slab.
+// Deterministic (no atomics): per-thread partials -> fixed-order reduction over threadIdx.y ->
+// fixed-order reduction over the channels of each group -> one partial per (image, chunk, group).
 __global__ void gn_stats_kernel(const GnParams p) {
-  extern __shared__ float s_acc[];  // [groups*2]
+  extern __shared__ float s_red[];  // [vy][vx][16] then col[2][C]
   const int img = blockIdx.y;
   const int cv = threadIdx.x;
   const int V = p.C >> 3;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int i = tid; i < p.groups * 2; i += blockDim.x * blockDim.y) s_acc[i] = 0.f;
-  __syncthreads();
+  const int vx = blockDim.x, vy = blockDim.y;
+  float* col = s_red + vy * vx * 16;
+  const int tid = threadIdx.y * vx + threadIdx.x;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
   if (cv < V) {
     const int ch = cv * 8;
     const bool from1 = ch >= p.c0;
@@ -60,16 +68,12 @@ __global__ void gn_stats_kernel(const GnParams p) {
     const int coff = from1 ? ch - p.c0 : ch;
     const int pbeg = blockIdx.x * p.pix_per_cta;
     const int pend = min(p.hw, pbeg + p.pix_per_cta);
-    float s[8], q[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
-    const int stepy = blockDim.y;
-    for (int px = pbeg + threadIdx.y; px < pend; px += 4 * stepy) {
+    for (int px = pbeg + threadIdx.y; px < pend; px += 4 * vy) {
       // four independent 16-byte loads in flight per thread
       uint4 raw[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int pp = px + u * stepy;
+        const int pp = px + u * vy;
         raw[u] = (pp < pend) ? *reinterpret_cast<const uint4*>(
                                    src + (static_cast<long long>(img) * p.hw + pp) * cs + coff)
                              : make_uint4(0, 0, 0, 0);
@@ -87,27 +91,37 @@ __global__ void gn_stats_kernel(const GnParams p) {
         }
       }
     }
-    // combine the (at most a few) groups this vector touches
-    int g_prev = ch / p.cpg;
-    float gs = 0.f, gq = 0.f;
+  }
+  float* mine = s_red + (threadIdx.y * vx + cv) * 16;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int g = (ch + e) / p.cpg;
-      if (g != g_prev) {
-        atomicAdd(&s_acc[g_prev * 2], gs);
-        atomicAdd(&s_acc[g_prev * 2 + 1], gq);
-        gs = gq = 0.f;
-        g_prev = g;
-      }
-      gs += s[e];
-      gq += q[e];
-    }
-    atomicAdd(&s_acc[g_prev * 2], gs);
-    atomicAdd(&s_acc[g_prev * 2 + 1], gq);
+  for (int e = 0; e < 8; ++e) {
+    mine[e] = s[e];
+    mine[8 + e] = q[e];
   }
   __syncthreads();
-  for (int i = tid; i < p.groups * 2; i += blockDim.x * blockDim.y)
-    atomicAdd(&p.ws[static_cast<long long>(img) * p.groups * 2 + i], static_cast<double>(s_acc[i]));
+  if (threadIdx.y == 0 && cv < V) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a = 0.f, b = 0.f;
+      for (int y = 0; y < vy; ++y) {
+        a += s_red[(y * vx + cv) * 16 + e];
+        b += s_red[(y * vx + cv) * 16 + 8 + e];
+      }
+      col[cv * 8 + e] = a;
+      col[p.C + cv * 8 + e] = b;
+    }
+  }
+  __syncthreads();
+  if (tid < p.groups) {
+    float a = 0.f, b = 0.f;
+    for (int c = tid * p.cpg; c < (tid + 1) * p.cpg; ++c) {
+      a += col[c];
+      b += col[p.C + c];
+    }
+    float* dst = p.ws + ((static_cast<long long>(img) * GN_MAX_CHUNKS + blockIdx.x) * p.groups + tid) * 2;
+    dst[0] = a;
+    dst[1] = b;
+  }
 }
 
 __global__ void gn_apply_kernel(const GnParams p) {
@@ -129,8 +143,12 @@ __global__ void gn_apply_kernel(const GnParams p) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int g = (ch + e) / p.cpg;
-      const double sum = p.ws[(static_cast<long long>(img) * p.groups + g) * 2];
-      const double sq = p.ws[(static_cast<long long>(img) * p.groups + g) * 2 + 1];
+      double sum = 0.0, sq = 0.0;
+      for (int k = 0; k < p.nchunks; ++k) {   // fixed order: deterministic
+        const float* part = p.ws + ((static_cast<long long>(img) * GN_MAX_CHUNKS + k) * p.groups + g) * 2;
+        sum += static_cast<double>(part[0]);
+        sq += static_cast<double>(part[1]);
+      }
       const double mean = sum / cnt;
       double var = sq / cnt - mean * mean;
       if (var < 0.0) var = 0.0;
@@ -295,7 +313,7 @@ static void launch_ln(const LnParams& p, int num_sms, cudaStream_t stream) {
 }  // namespace mdk
 
 extern "C" int64_t mdk_groupnorm_ws_bytes(int32_t nimg, int32_t groups) {
-  return static_cast<int64_t>(nimg) * groups * 2 * sizeof(double);
+  return static_cast<int64_t>(nimg) * mdk::GN_MAX_CHUNKS * groups * 2 * sizeof(float);
 }
 
 extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* stream_) {
@@ -325,7 +343,7 @@ extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* strea
   p.beta = static_cast<const __half*>(a->beta);
   p.silu = a->silu;
   p.out = static_cast<__half*>(a->out);
-  p.ws = static_cast<double*>(a->ws);
+  p.ws = static_cast<float*>(a->ws);
   const int V = C / 8;
   const int vx = ((V + 31) / 32) * 32;
   int vy = 512 / vx;
@@ -334,13 +352,17 @@ extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* strea
   int chunks = (ctx->num_sms * 4 + a->nimg - 1) / a->nimg;
   const int max_chunks = (a->hw + vy - 1) / vy;
   if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
   if (chunks < 1) chunks = 1;
   p.pix_per_cta = (a->hw + chunks - 1) / chunks;
   chunks = (a->hw + p.pix_per_cta - 1) / p.pix_per_cta;
-  MDK_CHECK_CUDA(cudaMemsetAsync(a->ws, 0, mdk_groupnorm_ws_bytes(a->nimg, a->groups), stream));
+  p.nchunks = chunks;
+  MDK_REQUIRE(a->groups <= vx * vy, "mdk_groupnorm_f16: too many groups");
   dim3 block(vx, vy);
   dim3 grid(chunks, a->nimg);
-  gn_stats_kernel<<<grid, block, a->groups * 2 * sizeof(float), stream>>>(p);
+  const size_t stats_smem = (static_cast<size_t>(vx) * vy * 16 + 2 * static_cast<size_t>(C)) * sizeof(float);
+  MDK_REQUIRE(stats_smem <= 48 * 1024, "mdk_groupnorm_f16: C=%d too large", C);
+  gn_stats_kernel<<<grid, block, stats_smem, stream>>>(p);
   count_launch();
   gn_apply_kernel<<<grid, block, 0, stream>>>(p);
   count_launch();

@@ -166,7 +166,8 @@ __global__ void temporal_attn_kernel(const TattnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tiled variant for the single-GPU layout (fused q|k|v rows [M, 3C], f_q == f_kv): a CTA owns PG
+// Tiled variant for the single-GPU layout (fused q|k|v rows [M, 3C], f_q == f_kv, PE already folded
+// into Q by the projection GEMM's row bias): a CTA owns PG
 // consecutive pixels of one batch entry, stages their f x 3C rows with fully coalesced 16-byte loads
 // (consecutive pixels of one frame are contiguous in memory), computes every (pixel, head) problem
 // from shared memory, overwrites the Q slots with O and writes the outputs back coalesced.
@@ -183,113 +184,170 @@ struct TattnTileParams {
   float scale_log2;
 };
 
-template <int FKV_MAX>
-__global__ void temporal_attn_tile_kernel(const TattnTileParams p) {
+__device__ __forceinline__ void mma_m16n8k16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                             uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];\n"
+               : "=r"(r0), "=r"(r1)
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory");
+}
+
+// One warp per (pixel, head) problem.  The tiny GEMMs run on the legacy mma.sync path on purpose:
+// a 16 x 16 x 40 problem cannot fill a tcgen05 128-row tile, the kernel is HBM-bound, and
+// m16n8k16 fragments can be fed straight from the staged rows (row stride 3C+8 halves makes every
+// fragment load bank-conflict free).  MT = number of 16-row query tiles (frames padded to 16*MT).
+template <int MT>
+__global__ void __launch_bounds__(256) temporal_attn_tile_kernel(const TattnTileParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __half* sm = reinterpret_cast<__half*>(smem_raw);
+  constexpr int FP = 16 * MT;
   const int groups_per_b = (p.npix + p.pg - 1) / p.pg;
   const int b = blockIdx.x / groups_per_b;
   const int px0 = (blockIdx.x % groups_per_b) * p.pg;
   const int npx = min(p.pg, p.npix - px0);
   const int rowv = (3 * p.C) >> 3;  // 16-byte vectors per row
   // ---- coalesced load: for each frame the npx pixel rows are one contiguous run ----
-  for (int j = 0; j < p.f; ++j) {
+  for (int j = 0; j < FP; ++j) {
     const __half* src = p.qkv + ((static_cast<long long>(b) * p.f + j) * p.npix + px0) * p.ld;
     for (int i = threadIdx.x; i < npx * rowv; i += blockDim.x) {
       const int px = i / rowv, v = i % rowv;
-      *reinterpret_cast<uint4*>(sm + (static_cast<long long>(px) * p.f + j) * p.rs + v * 8) =
-          *reinterpret_cast<const uint4*>(src + static_cast<long long>(px) * p.ld + v * 8);
+      uint4 val = make_uint4(0, 0, 0, 0);                 // frames >= f: zero rows (P is 0 there)
+      if (j < p.f) val = *reinterpret_cast<const uint4*>(src + static_cast<long long>(px) * p.ld + v * 8);
+      *reinterpret_cast<uint4*>(sm + (static_cast<long long>(px) * FP + j) * p.rs + v * 8) = val;
     }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-  const int ppw = 32 / p.qpw;
+  const int g = lane >> 2, t = lane & 3;
   const int nprob = npx * p.heads;
-  const int dv = p.d >> 3;
-  for (int g = warp; g * ppw < nprob; g += warps) {
-    const int pr = g * ppw + lane / p.qpw;
-    const int i = lane % p.qpw;
-    if (pr < nprob && i < p.f) {
-      const int px = pr / p.heads, h = pr % p.heads;
-      __half* base = sm + static_cast<long long>(px) * p.f * p.rs;
-      __half* qrow = base + static_cast<long long>(i) * p.rs + h * p.d;
-      const __half* k0 = base + p.C + h * p.d;
-      const __half* v0 = base + 2 * p.C + h * p.d;
-      const float* peptr = p.pe_q ? p.pe_q + static_cast<long long>(i) * p.C + h * p.d : nullptr;
-      float s[FKV_MAX];
+  const int ksteps = (p.d + 15) >> 4;
+  const bool half_last = (p.d & 15) != 0;  // d % 16 == 8: upper half of the last K step is padding
+  const int ntile_o = p.d >> 3;
+  const uint32_t sm_base = smem_u32(sm);
+  const uint32_t rsb = static_cast<uint32_t>(p.rs) * 2u;  // row stride in bytes
+  for (int pr = warp; pr < nprob; pr += warps) {
+    const int px = pr / p.heads, h = pr % p.heads;
+    const uint32_t qb = sm_base + (static_cast<uint32_t>(px) * FP * p.rs + h * p.d) * 2u;
+    const uint32_t kb = qb + static_cast<uint32_t>(p.C) * 2u;
+    const uint32_t vb = qb + static_cast<uint32_t>(p.C) * 4u;
+    // ---- S = Q K^T ----
+    float sacc[MT][2 * MT][4];
 #pragma unroll
-      for (int j = 0; j < FKV_MAX; ++j) s[j] = 0.f;
-      for (int v = 0; v < dv; ++v) {
-        float qv[8];
-        {
-          uint4 raw = *reinterpret_cast<const uint4*>(qrow + v * 8);
-          const __half2* hq = reinterpret_cast<const __half2*>(&raw);
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float2 f2 = __half22float2(hq[e]);
-            qv[2 * e] = f2.x;
-            qv[2 * e + 1] = f2.y;
+      for (int nt = 0; nt < 2 * MT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sacc[mt][nt][e] = 0.f;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const bool pad_hi = half_last && ks == ksteps - 1;
+      const uint32_t col = static_cast<uint32_t>(ks * 16 + 2 * t) * 2u;
+      uint32_t bfr[2 * MT][2];
+#pragma unroll
+      for (int nt = 0; nt < 2 * MT; ++nt) {
+        const uint32_t ra = kb + static_cast<uint32_t>(nt * 8 + g) * rsb + col;
+        bfr[nt][0] = lds32(ra);
+        bfr[nt][1] = pad_hi ? 0u : lds32(ra + 16);
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        uint32_t a[4];
+        const uint32_t r0 = qb + static_cast<uint32_t>(mt * 16 + g) * rsb + col;
+        a[0] = lds32(r0);
+        a[1] = lds32(r0 + 8 * rsb);
+        a[2] = pad_hi ? 0u : lds32(r0 + 16);
+        a[3] = pad_hi ? 0u : lds32(r0 + 8 * rsb + 16);
+#pragma unroll
+        for (int nt = 0; nt < 2 * MT; ++nt) mma_m16n8k16(sacc[mt][nt], a, bfr[nt][0], bfr[nt][1]);
+      }
+    }
+    // ---- softmax over the keys (columns), rows g and g+8 of each query tile ----
+    uint32_t pfr[MT][MT][4];  // P as the A operand of the P V MMAs: [query tile][key k-step]
+    float inv_l[MT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 2 * MT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool valid = nt * 8 + 2 * t + e < p.f;
+          if (!valid) {
+            sacc[mt][nt][e] = -INFINITY;
+            sacc[mt][nt][2 + e] = -INFINITY;
           }
-          if (peptr) {
-            const float4 a = *reinterpret_cast<const float4*>(peptr + v * 8);
-            const float4 c = *reinterpret_cast<const float4*>(peptr + v * 8 + 4);
-            qv[0] += a.x; qv[1] += a.y; qv[2] += a.z; qv[3] += a.w;
-            qv[4] += c.x; qv[5] += c.y; qv[6] += c.z; qv[7] += c.w;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < FKV_MAX; ++j) {
-          if (j < p.f) {
-            uint4 raw = *reinterpret_cast<const uint4*>(k0 + static_cast<long long>(j) * p.rs + v * 8);
-            const __half2* hk = reinterpret_cast<const __half2*>(&raw);
-            float a = s[j];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f2 = __half22float2(hk[e]);
-              a = fmaf(qv[2 * e], f2.x, a);
-              a = fmaf(qv[2 * e + 1], f2.y, a);
-            }
-            s[j] = a;
-          }
+          mx0 = fmaxf(mx0, sacc[mt][nt][e]);
+          mx1 = fmaxf(mx1, sacc[mt][nt][2 + e]);
         }
       }
-      float mx = -INFINITY;
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < FKV_MAX; ++j)
-        if (j < p.f) mx = fmaxf(mx, s[j]);
-      float l = 0.f;
+      for (int nt = 0; nt < 2 * MT; ++nt) {
 #pragma unroll
-      for (int j = 0; j < FKV_MAX; ++j) {
-        if (j < p.f) {
-          s[j] = exp2f((s[j] - mx) * p.scale_log2);
-          l += s[j];
+        for (int e = 0; e < 2; ++e) {
+          const float p0 = exp2f((sacc[mt][nt][e] - mx0) * p.scale_log2);
+          const float p1 = exp2f((sacc[mt][nt][2 + e] - mx1) * p.scale_log2);
+          sacc[mt][nt][e] = p0;
+          sacc[mt][nt][2 + e] = p1;
+          l0 += p0;
+          l1 += p1;
         }
       }
-      const float inv = 1.0f / l;
-      for (int v = 0; v < dv; ++v) {
-        float o[8];
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      inv_l[mt][0] = 1.0f / l0;
+      inv_l[mt][1] = 1.0f / l1;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+      for (int kk = 0; kk < MT; ++kk) {
+        pfr[mt][kk][0] = pack_half2(sacc[mt][2 * kk][0], sacc[mt][2 * kk][1]);
+        pfr[mt][kk][1] = pack_half2(sacc[mt][2 * kk][2], sacc[mt][2 * kk][3]);
+        pfr[mt][kk][2] = pack_half2(sacc[mt][2 * kk + 1][0], sacc[mt][2 * kk + 1][1]);
+        pfr[mt][kk][3] = pack_half2(sacc[mt][2 * kk + 1][2], sacc[mt][2 * kk + 1][3]);
+      }
+    }
+    // ---- O = P V, written over the (dead) query slot of this head ----
+    __syncwarp();
+    for (int nt = 0; nt < ntile_o; ++nt) {
+      float oacc[MT][4];
 #pragma unroll
-        for (int j = 0; j < FKV_MAX; ++j) {
-          if (j < p.f) {
-            uint4 raw = *reinterpret_cast<const uint4*>(v0 + static_cast<long long>(j) * p.rs + v * 8);
-            const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f2 = __half22float2(hv[e]);
-              o[2 * e] = fmaf(s[j], f2.x, o[2 * e]);
-              o[2 * e + 1] = fmaf(s[j], f2.y, o[2 * e + 1]);
-            }
-          }
-        }
-        uint4 pk;
-        pk.x = pack_half2(o[0] * inv, o[1] * inv);
-        pk.y = pack_half2(o[2] * inv, o[3] * inv);
-        pk.z = pack_half2(o[4] * inv, o[5] * inv);
-        pk.w = pack_half2(o[6] * inv, o[7] * inv);
-        // the query slot of this (frame, head) is dead: reuse it for the output row
-        *reinterpret_cast<uint4*>(qrow + v * 8) = pk;
+        for (int e = 0; e < 4; ++e) oacc[mt][e] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < MT; ++kk) {
+        uint32_t b0, b1;
+        // lanes 0-15 address the 16 key rows of this k-step (8 channels starting at nt*8)
+        ldmatrix_x2_trans(vb + static_cast<uint32_t>(kk * 16 + (lane & 15)) * rsb +
+                              static_cast<uint32_t>(nt * 8) * 2u,
+                          b0, b1);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) mma_m16n8k16(oacc[mt], pfr[mt][kk], b0, b1);
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t o0 = qb + static_cast<uint32_t>(mt * 16 + g) * rsb +
+                            static_cast<uint32_t>(nt * 8 + 2 * t) * 2u;
+        sts32(o0, pack_half2(oacc[mt][0] * inv_l[mt][0], oacc[mt][1] * inv_l[mt][0]));
+        sts32(o0 + 8 * rsb, pack_half2(oacc[mt][2] * inv_l[mt][1], oacc[mt][3] * inv_l[mt][1]));
       }
     }
   }
@@ -301,7 +359,7 @@ __global__ void temporal_attn_tile_kernel(const TattnTileParams p) {
     for (int i = threadIdx.x; i < npx * outv; i += blockDim.x) {
       const int px = i / outv, v = i % outv;
       *reinterpret_cast<uint4*>(dst + static_cast<long long>(px) * p.out_ld + v * 8) =
-          *reinterpret_cast<const uint4*>(sm + (static_cast<long long>(px) * p.f + j) * p.rs + v * 8);
+          *reinterpret_cast<const uint4*>(sm + (static_cast<long long>(px) * FP + j) * p.rs + v * 8);
     }
   }
 }
@@ -328,11 +386,12 @@ extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void
                        a->q_ld == a->kv_ld && a->q_ld >= 3 * C && a->f_q == a->f_kv &&
                        f_kv_rank == a->f_kv && a->f_q_offset == 0;
     const int rs = 3 * C + 8;
-    const size_t per_px = static_cast<size_t>(a->f_q) * rs * sizeof(__half);
-    if (fused && per_px <= 200 * 1024) {
+    const int fp = a->f_q <= 16 ? 16 : 32;
+    const size_t per_px = static_cast<size_t>(fp) * rs * sizeof(__half);
+    if (fused && a->pe_q == nullptr && per_px <= 200 * 1024) {
       TattnTileParams t;
       t.qkv = static_cast<const __half*>(a->q);
-      t.pe_q = a->pe_q;
+      t.pe_q = nullptr;
       t.out = static_cast<__half*>(a->out);
       t.ld = a->q_ld;
       t.out_ld = a->out_ld;
@@ -356,17 +415,17 @@ extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void
       const int groups = (a->npix + pg - 1) / pg;
       static bool tile_attr = false;
       if (!tile_attr) {
-        MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_tile_kernel<16>,
+        MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_tile_kernel<1>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_tile_kernel<32>,
+        MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_tile_kernel<2>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         tile_attr = true;
       }
       const unsigned grid = static_cast<unsigned>(a->nb) * groups;
       if (a->f_q <= 16)
-        temporal_attn_tile_kernel<16><<<grid, 256, smem, stream>>>(t);
+        temporal_attn_tile_kernel<1><<<grid, 256, smem, stream>>>(t);
       else
-        temporal_attn_tile_kernel<32><<<grid, 256, smem, stream>>>(t);
+        temporal_attn_tile_kernel<2><<<grid, 256, smem, stream>>>(t);
       count_launch();
       MDK_CHECK_CUDA(cudaGetLastError());
       return 0;

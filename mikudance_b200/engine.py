@@ -157,8 +157,11 @@ class UNetEngine:
             e.wo, e.bo = _f16(ab.to_out[0].weight, dev), _f32(ab.to_out[0].bias, dev)
             # PE enters the query only (motion_module.py:404-417): (x + pe) Wq^T = x Wq^T + pe Wq^T.
             # The table pe @ Wq^T is a constant of the weights: computed once here in fp32 on the GPU.
+            # It rides on the fused q|k|v GEMM as a per-frame row bias (zero for the k and v columns), so
+            # the query gets it in fp32 before its single fp16 rounding.
             pe = ab.pos_encoder.pe.detach().to(device=dev, dtype=F32)[0]
-            e.pe_q = (pe @ wq.float().t()).contiguous()
+            e.pe_qkv = torch.zeros((pe.shape[0], 3 * o.c), dtype=F32, device=dev)
+            e.pe_qkv[:, : o.c] = pe @ wq.float().t()
             o.att.append(e)
         o.ffnw, o.ffnb = _f16(blk.ff_norm.weight, dev), _f16(blk.ff_norm.bias, dev)
         self._pack_ff(blk.ff, o)
@@ -284,19 +287,19 @@ class UNetEngine:
         h = ops.gemm(h, o.pin_w, bias=o.pin_b)
         for e in o.att:
             n = ops.layernorm(h, e.lnw, e.lnb)
+            pe_rows = e.pe_qkv[f_off:f_off + fl]        # frame j of this shard sits at window position f_off+j
             if self.world == 1:
-                qkv = ops.gemm(n, e.wqkv)
-                a = ops.temporal_attention(qkv, nb=nb, f_q=fl, npix=hw, heads=self.mheads, d=d,
-                                           pe_q=e.pe_q)
+                qkv = ops.gemm(n, e.wqkv, row_bias=pe_rows, row_div=hw)
+                a = ops.temporal_attention(qkv, nb=nb, f_q=fl, npix=hw, heads=self.mheads, d=d)
             else:
                 import torch.distributed as dist
                 qb = torch.empty((N * hw, C), dtype=F16, device=self.dev)
                 kv = torch.empty((N * hw, 2 * C), dtype=F16, device=self.dev)
-                ops.gemm(n, e.wqkv, outs=[qb, kv[:, :C], kv[:, C:]])
+                ops.gemm(n, e.wqkv, outs=[qb, kv[:, :C], kv[:, C:]], row_bias=pe_rows, row_div=hw)
                 kv_all = torch.empty((self.world * N * hw, 2 * C), dtype=F16, device=self.dev)
                 dist.all_gather_into_tensor(kv_all, kv, group=self.pg)   # NCCL over NVLink
                 a = ops.temporal_attention(qb, nb=nb, f_q=fl, npix=hw, heads=self.mheads, d=d,
-                                           pe_q=e.pe_q, kv=kv_all, f_kv=f_total, f_kv_rank=fl,
+                                           kv=kv_all, f_kv=f_total, f_kv_rank=fl,
                                            f_q_offset=f_off, kv_offsets=(0, C))
             h = ops.gemm(a, e.wo, bias=e.bo, residual=h)
         h = self._ff(o, h, o.ffnw, o.ffnb)

@@ -204,7 +204,7 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, nimg
     if out is None:
         out = torch.empty((nimg * hw, c0 + c1), dtype=F16, device=dev)
     if ws is None:
-        ws = torch.empty((nimg * groups * 2,), dtype=torch.float64, device=dev)
+        ws = torch.empty((load_library().mdk_groupnorm_ws_bytes(nimg, groups),), dtype=torch.uint8, device=dev)
     a = GnArgs()
     a.x0, a.c0 = ptr(x0), c0
     if x1 is not None:

@@ -208,6 +208,14 @@ def check_temporal():
         out = ops.temporal_attention(qkv, nb=nb, f_q=f, npix=npix, heads=heads, d=d, pe_q=pe)
         ref = ref_temporal(qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:], pe, nb, f, npix, heads, d)
         ok &= report(f"temporal nb={nb} f={f} npix={npix} h={heads} d={d}", out, ref)
+    # tensor-core tile path (no PE inside the kernel: the engine folds it into the q|k|v GEMM)
+    for (nb, f, npix, heads, d) in [(2, 16, 150, 8, 40), (2, 4, 64, 8, 8), (1, 30, 37, 8, 80),
+                                    (2, 32, 16, 8, 160), (2, 7, 50, 4, 16), (2, 16, 9216, 8, 40)]:
+        C_ = heads * d
+        qkv = rnd(nb * f * npix, 3 * C_).to(F16)
+        out = ops.temporal_attention(qkv, nb=nb, f_q=f, npix=npix, heads=heads, d=d)
+        ref = ref_temporal(qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:], None, nb, f, npix, heads, d)
+        ok &= report(f"temporal(tile) nb={nb} f={f} npix={npix} h={heads} d={d}", out, ref)
     # sharded layout: 2 "ranks" x f_local frames gathered
     nb, f, npix, heads, d = 2, 8, 40, 8, 40
     C_ = heads * d
@@ -396,6 +404,28 @@ def perf_gemm_small():
     return True
 
 
+def perf_misc():
+    warm_gpu()
+    for (nb, f, npix, heads, d) in [(2, 16, 9216, 8, 40), (2, 16, 2304, 8, 80), (2, 16, 576, 8, 160)]:
+        C_ = heads * d
+        qkv = rnd(nb * f * npix, 3 * C_).to(F16)
+        out = torch.empty(nb * f * npix, C_, dtype=F16, device=DEV)
+        ms = timeit_ms(lambda: ops.temporal_attention(qkv, nb=nb, f_q=f, npix=npix, heads=heads, d=d, out=out))
+        by = 2.0 * nb * f * npix * C_ * 4
+        print(f"perf temporal f={f} npix={npix} d={d}: {ms:.3f} ms  {by / ms / 1e6:.0f} GB/s", flush=True)
+    for (nimg, hw, c) in [(32, 9216, 320), (32, 2304, 640), (32, 576, 1280)]:
+        x = rnd(nimg * hw, c).to(F16)
+        gm = (1 + 0.1 * rnd(c)).to(F16)
+        bt = (0.1 * rnd(c, seed=4)).to(F16)
+        out = torch.empty_like(x)
+        ws = torch.empty(2 ** 21, dtype=torch.uint8, device=DEV)
+        ms = timeit_ms(lambda: ops.groupnorm(x, gm, bt, nimg=nimg, hw=hw, groups=32, eps=1e-5, silu=True, out=out, ws=ws))
+        print(f"perf groupnorm n={nimg} hw={hw} c={c}: {ms:.3f} ms  {3 * 2.0 * x.numel() / ms / 1e6:.0f} GB/s", flush=True)
+        ms = timeit_ms(lambda: ops.layernorm(x, gm, bt, out=out))
+        print(f"perf layernorm rows={nimg * hw} c={c}: {ms:.3f} ms  {2 * 2.0 * x.numel() / ms / 1e6:.0f} GB/s", flush=True)
+    return True
+
+
 def perf_attn():
     warm_gpu()
     for (nimg, l, heads, d) in [(8, 9216, 8, 40), (32, 2304, 8, 80), (32, 576, 8, 160)]:
@@ -473,7 +503,7 @@ CHECKS = {
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
     "norms": check_norms, "temporal": check_temporal, "misc": check_misc, "attn": check_attn,
-    "perf_gemm": perf_gemm, "perf_attn": perf_attn, "ncu_gemm": ncu_gemm, "perf_gemm_small": perf_gemm_small, "ncu_attn": ncu_attn,
+    "perf_gemm": perf_gemm, "perf_attn": perf_attn, "ncu_gemm": ncu_gemm, "perf_gemm_small": perf_gemm_small, "perf_misc": perf_misc, "ncu_attn": ncu_attn,
 }
 
 if __name__ == "__main__":
