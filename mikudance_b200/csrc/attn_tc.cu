@@ -22,6 +22,10 @@ namespace mdk {
 constexpr int ATT_BQ = 128;
 constexpr int ATT_THREADS = 192;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
+#ifndef MDK_ATT_POLY_EXP
+#define MDK_ATT_POLY_EXP 0
+#endif
+constexpr bool ATT_POLY_EXP = MDK_ATT_POLY_EXP != 0;
 
 // exp2 on the FMA/ALU pipes (Cody-Waite reduction + degree-3 minimax polynomial, max relative error
 // 7.5e-5 — below the fp16 rounding P gets anyway).  The d=40 self-attention is bound by the MUFU
@@ -284,7 +288,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
             const float p0 =
                 ex2_approx(fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e]), p.scale_log2, -m_used));
             const float x1 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used);
-            const float p1 = (e & 1) ? ex2_poly3(x1) : ex2_approx(x1);   // 2 of every 8 on the FMA pipe
+            // ATT_POLY_EXP: measured slower at the current MUFU utilisation (62 %): off by default
+            const float p1 = (ATT_POLY_EXP && (e & 1)) ? ex2_poly3(x1) : ex2_approx(x1);
             rs += p0 + p1;
             pk[e] = pack_half2(p0, p1);
           }

@@ -128,33 +128,40 @@ __global__ void gn_apply_kernel(const GnParams p) {
   const int img = blockIdx.y;
   const int cv = threadIdx.x;
   const int V = p.C >> 3;
-  if (cv >= V) return;
   const int ch = cv * 8;
   const bool from1 = ch >= p.c0;
   const __half* src = from1 ? p.x1 : p.x0;
   const int cs = from1 ? p.c1 : p.c0;
   const int coff = from1 ? ch - p.c0 : ch;
+  // mean / rstd of every group: combined once per CTA from the per-chunk partials (fixed order, fp64)
+  __shared__ float s_mean[64], s_rstd[64];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < p.groups) {
+    double sum = 0.0, sq = 0.0;
+    for (int k = 0; k < p.nchunks; ++k) {
+      const float* part = p.ws + ((static_cast<long long>(img) * GN_MAX_CHUNKS + k) * p.groups + tid) * 2;
+      sum += static_cast<double>(part[0]);
+      sq += static_cast<double>(part[1]);
+    }
+    const double cnt = static_cast<double>(p.hw) * p.cpg;
+    const double mean = sum / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = static_cast<float>(mean);
+    s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+  }
+  __syncthreads();
+  if (cv >= V) return;
   float scale[8], shift[8];
   {
     float gm[8], bt[8];
     load8(p.gamma + ch, gm);
     load8(p.beta + ch, bt);
-    const double cnt = static_cast<double>(p.hw) * p.cpg;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int g = (ch + e) / p.cpg;
-      double sum = 0.0, sq = 0.0;
-      for (int k = 0; k < p.nchunks; ++k) {   // fixed order: deterministic
-        const float* part = p.ws + ((static_cast<long long>(img) * GN_MAX_CHUNKS + k) * p.groups + g) * 2;
-        sum += static_cast<double>(part[0]);
-        sq += static_cast<double>(part[1]);
-      }
-      const double mean = sum / cnt;
-      double var = sq / cnt - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
-      scale[e] = gm[e] * rstd;
-      shift[e] = bt[e] - static_cast<float>(mean) * scale[e];
+      scale[e] = gm[e] * s_rstd[g];
+      shift[e] = bt[e] - s_mean[g] * scale[e];
     }
   }
   const int pbeg = blockIdx.x * p.pix_per_cta;
@@ -183,7 +190,7 @@ __global__ void gn_apply_kernel(const GnParams p) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           float y = v[e] * scale[e] + shift[e];
-          if (p.silu) y = y / (1.0f + __expf(-y));
+          if (p.silu) y = __fdividef(y, 1.0f + __expf(-y));
           v[e] = y;
         }
         store8(p.out + (static_cast<long long>(img) * p.hw + pp) * p.C + ch, v);
@@ -324,6 +331,7 @@ extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* strea
   const int C = a->c0 + a->c1;
   MDK_REQUIRE(a->c0 % 8 == 0 && a->c1 % 8 == 0 && C > 0, "mdk_groupnorm_f16: c0=%d c1=%d must be %%8",
               a->c0, a->c1);
+  MDK_REQUIRE(a->groups <= 64, "mdk_groupnorm_f16: at most 64 groups");
   MDK_REQUIRE(a->groups > 0 && C % a->groups == 0, "mdk_groupnorm_f16: C=%d not divisible by groups=%d",
               C, a->groups);
   MDK_REQUIRE(C / 8 <= 1024, "mdk_groupnorm_f16: C=%d too large", C);
@@ -349,7 +357,7 @@ extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* strea
   int vy = 512 / vx;
   if (vy < 1) vy = 1;
   // enough CTAs to fill the machine a few times over, at least one pixel row of work each
-  int chunks = (ctx->num_sms * 4 + a->nimg - 1) / a->nimg;
+  int chunks = (ctx->num_sms * 8 + a->nimg - 1) / a->nimg;
   const int max_chunks = (a->hw + vy - 1) / vy;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;

@@ -361,6 +361,35 @@ def ncu_gemm():
     return True
 
 
+def ncu_gemm2():
+    """L0 transformer linears for an ncu capture: out-projection (bias + residual) and GEGLU."""
+    M, K = 294912, 320
+    a = rnd(M, K).to(F16)
+    w = rnd(320, K, scale=K ** -0.5).to(F16)
+    bias = rnd(320)
+    res = rnd(M, 320).to(F16)
+    out = torch.empty(M, 320, dtype=F16, device=DEV)
+    wg = rnd(2560, K, scale=K ** -0.5).to(F16)
+    bg = rnd(2560)
+    outg = torch.empty(M, 1280, dtype=F16, device=DEV)
+    warm_gpu(1.0)
+    for _ in range(3):
+        ops.gemm(a, w, bias=bias, residual=res, out=out)
+        ops.gemm(a, wg, bias=bg, geglu=True, out=outg)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ops.gemm(a, w, bias=bias, residual=res, out=out)
+    e1.record()
+    for _ in range(20):
+        ops.gemm(a, wg, bias=bg, geglu=True, out=outg)
+    e2.record()
+    torch.cuda.synchronize()
+    print(f"perf outproj(bias+res) {e0.elapsed_time(e1) / 20:.3f} ms   geglu {e1.elapsed_time(e2) / 20:.3f} ms", flush=True)
+    return True
+
+
 def ncu_attn():
     nimg, l, heads, d = 2, 9216, 8, 40
     C_ = heads * d
@@ -503,7 +532,7 @@ CHECKS = {
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
     "norms": check_norms, "temporal": check_temporal, "misc": check_misc, "attn": check_attn,
-    "perf_gemm": perf_gemm, "perf_attn": perf_attn, "ncu_gemm": ncu_gemm, "perf_gemm_small": perf_gemm_small, "perf_misc": perf_misc, "ncu_attn": ncu_attn,
+    "perf_gemm": perf_gemm, "perf_attn": perf_attn, "ncu_gemm": ncu_gemm, "ncu_gemm2": ncu_gemm2, "perf_gemm_small": perf_gemm_small, "perf_misc": perf_misc, "ncu_attn": ncu_attn,
 }
 
 if __name__ == "__main__":

@@ -1,0 +1,73 @@
+"""Multi-GPU parity (run under torchrun on N GPUs of one box, not collected by pytest):
+frame-sharded DenoiseLoop (NCCL all-gather of temporal K/V, all-reduce of the window accumulators)
+against the single-GPU loop on identical inputs.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+      --master-port 29511 tests/multigpu_check.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from mikudance_b200 import synth
+    from mikudance_b200.denoise import DenoiseLoop
+    from mikudance_b200.scheduler import DDIMScheduler
+    from mikudance_b200.unet_3d import UNet3DConditionModel
+    cfg = synth.TINY_CONFIG
+    m = UNet3DConditionModel(block_out_channels=cfg["block_out_channels"],
+                             cross_attention_dim=cfg["cross_attention_dim"], use_inflated_groupnorm=True,
+                             use_motion_module=True, motion_module_mid_block=True, motion_module_type="Vanilla",
+                             motion_module_kwargs=dict(temporal_position_encoding=True,
+                                                       temporal_position_encoding_max_len=32),
+                             unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+    m.load_state_dict(synth.synthetic_state_dict(cfg, seed=0))
+    m = m.to(device=dev, dtype=torch.float16).eval()
+    kw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", clip_sample=False, steps_offset=1,
+              prediction_type="v_prediction", rescale_betas_zero_snr=True, timestep_spacing="trailing")
+    ok = True
+    for (F_, ctxf, ov) in [(4 * world, 30, 8), (6 * world, 4 * world, 2 * world)]:
+        h = w = 16
+        lat, ctx = synth.synthetic_inputs(cfg, 2, F_, h, w, lctx=9)
+        lat = lat[:1].half()
+
+        def banks_for_window(wdw):
+            return synth.synthetic_banks(cfg, 2 * len(wdw), h, w, seed=300 + wdw[0])
+
+        res = {}
+        for name, pg, graph in (("single", None, True), ("sharded", dist.group.WORLD, True),
+                                ("sharded-eager", dist.group.WORLD, False)):
+            loop = DenoiseLoop(m, DDIMScheduler(**kw), guidance_scale=3.5, context_frames=ctxf,
+                               context_stride=1, context_overlap=ov, process_group=pg, use_cuda_graph=graph)
+            loop.prepare(lat.to(dev).contiguous().clone(), ctx, 3, banks_for_window)
+            res[name] = loop.run().float().cpu()
+            torch.cuda.synchronize()
+            dist.barrier()
+        rel = ((res["sharded"] - res["single"]).norm() / res["single"].norm()).item()
+        same = torch.equal(res["sharded"], res["sharded-eager"])
+        flag = torch.tensor([1.0 if (rel < 3e-3 and same) else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # every rank must agree (latents are replicated)
+        ok &= bool(flag.item() > 0.5)
+        if rank == 0:
+            print(f"F={F_} ctx={ctxf}: windows={[len(x) for x in loop.windows]} sharded-vs-single rel_l2={rel:.3e} "
+                  f"graph==eager {same}", flush=True)
+            ok &= rel < 3e-3 and same
+    if rank == 0:
+        print("MULTIGPU", "PASS" if ok else "FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
