@@ -243,10 +243,16 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           }
         }
       }
+      {
+        // 4 independent running maxima: a single fmaxf chain over 128 scores is 128 x 4 cycles of
+        // pure dependency latency per tile
+        float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
+        for (int c = 0; c < BKV / 32; ++c) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[c][e]));
+          for (int e = 0; e < 32; ++e) mp[e & 3] = fmaxf(mp[e & 3], __uint_as_float(v[c][e]));
+        }
+        mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
       }
       mx *= p.scale_log2;
       float alpha = 1.0f;
@@ -277,7 +283,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       }
       // exp2, row sum, fp16 pack and the store of P, 8 columns (one 16-byte piece) at a time.
       // P -> smem, K-major, 128B swizzle: 16-byte piece q of row r lands at piece (q ^ (r & 7))
-      float rs = 0.f;
+      float rsp[2] = {0.f, 0.f};  // independent partial row sums (short dependency chains)
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) {
 #pragma unroll
@@ -290,7 +296,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
             const float x1 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used);
             // ATT_POLY_EXP: measured slower at the current MUFU utilisation (62 %): off by default
             const float p1 = (ATT_POLY_EXP && (e & 1)) ? ex2_poly3(x1) : ex2_approx(x1);
-            rs += p0 + p1;
+            rsp[e & 1] += p0 + p1;
             pk[e] = pack_half2(p0, p1);
           }
           const uint32_t col8 = c * 4 + q4;   // 8-column piece index inside the BKV tile
@@ -298,7 +304,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           st_shared_v4(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
       }
-      l_sum += rs;
+      l_sum += rsp[0] + rsp[1];
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();

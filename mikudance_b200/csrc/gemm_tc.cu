@@ -31,6 +31,9 @@ constexpr int EPI_WARPS = 8;
 
 struct GemmParams {
   CUtensorMap tmA0, tmA1, tmB;
+  CUtensorMap tmO[3];  // output segments for the TMA-store epilogue (box 32 cols x 32 rows, 64B swizzle)
+  int tma_store;       // 1: epilogue writes through TMA stores, 0: smem transpose + st.global
+  int sbw, sbh, sbn;   // conv: the 32-row sub-box a warp stores
   int M, N;
   int kb0, kb1;  // 64-wide K blocks (per tap) from source 0 / 1
   int k0;        // K extent of source 0 (B column offset of source 1 inside a tap)
@@ -57,8 +60,8 @@ template <int BN>
 struct GemmCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 160 ? 5 : 6);
-  static constexpr int EPI_STAGING = EPI_WARPS * 32 * 64;  // per epilogue warp: 32 rows x 32 fp16
+  static constexpr int STAGES = (BN >= 192) ? 4 : (BN >= 160 ? 5 : 6);
+  static constexpr int EPI_STAGING = EPI_WARPS * 2 * 32 * 64;  // per epilogue warp: 2 x (32 rows x 32 fp16)
   static constexpr int TMEM_COLS = (2 * BN <= 32)    ? 32
                                    : (2 * BN <= 64)  ? 64
                                    : (2 * BN <= 128) ? 128
@@ -114,6 +117,32 @@ __device__ __forceinline__ void store_chunk_coalesced(const float (&o)[32], uint
       *reinterpret_cast<uint4*>(obase + static_cast<long long>(m_r) * ldo + col0 + q * 8) = val;
   }
   __syncwarp();
+}
+
+// TMA-store variant: the sub-tile goes to a (double-buffered) staging buffer in the 64B-swizzled
+// layout and one elected lane issues an asynchronous bulk tensor store; bounds are clipped by TMA.
+__device__ __forceinline__ void store_chunk_tma(const float (&o)[32], uint32_t buf_addr, int lane,
+                                                const CUtensorMap* tm, bool conv, int c0, int c1, int c2,
+                                                int c3) {
+  if (lane == 0) bulk_wait_read<1>();  // the store that last read this buffer has drained
+  __syncwarp();
+  const uint32_t my = buf_addr + static_cast<uint32_t>(lane) * 64u;
+  const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+#pragma unroll
+  for (uint32_t q = 0; q < 4; ++q) {
+    st_shared_v4(my + ((q ^ sw) << 4), pack_half2(o[q * 8 + 0], o[q * 8 + 1]),
+                 pack_half2(o[q * 8 + 2], o[q * 8 + 3]), pack_half2(o[q * 8 + 4], o[q * 8 + 5]),
+                 pack_half2(o[q * 8 + 6], o[q * 8 + 7]));
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (conv)
+      tma_store_4d(tm, buf_addr, c0, c1, c2, c3);
+    else
+      tma_store_2d(tm, buf_addr, c0, c1);
+    bulk_commit();
+  }
 }
 
 template <int BN>
@@ -250,7 +279,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
     const int cgroup = (warp - 2) >> 2;     // 0/1: which half of the 32-column chunks this warp takes
     const int row_in_tile = quarter * 32 + lane;
-    const uint32_t stage_addr = smem_u32(smem_epi) + static_cast<uint32_t>(warp - 2) * 2048u;
+    const uint32_t stage_addr = smem_u32(smem_epi) + static_cast<uint32_t>(warp - 2) * 4096u;
+    uint32_t tma_buf = 0;  // which of the warp's two staging buffers the next TMA store uses
     uint32_t acc_phase[2] = {0, 0};
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -273,6 +303,19 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       } else {
         m = static_cast<long long>(m_tile) * BM + row_in_tile;
         if (m >= p.M) m = -1;
+      }
+      // TMA-store coordinates of this warp's 32-row sub-tile
+      int tc1, tc2 = 0, tc3 = 0;
+      if (p.taps > 1) {
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int r0 = quarter * 32;
+        tc1 = tw * p.bw;
+        tc2 = th * p.bh + (r0 / p.bw) % p.bh;
+        tc3 = tn * p.bn + r0 / (p.bw * p.bh);
+      } else {
+        tc1 = m_tile * BM + quarter * 32;
       }
       const float* rb = nullptr;
       if (p.row_bias != nullptr && m >= 0)
@@ -322,8 +365,15 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
               }
             }
           }
-          if (!(p.dbg & 1))
-            store_chunk_coalesced(o, stage_addr, lane, m32, p.out[0], p.ldo[0], ocol0 + c, 32);
+          if (!(p.dbg & 1)) {
+            if (p.tma_store) {
+              store_chunk_tma(o, stage_addr + tma_buf * 2048u, lane, &p.tmO[0], p.taps > 1, ocol0 + c, tc1,
+                              tc2, tc3);
+              tma_buf ^= 1u;
+            } else {
+              store_chunk_coalesced(o, stage_addr, lane, m32, p.out[0], p.ldo[0], ocol0 + c, 32);
+            }
+          }
         }
       } else {
         const int seg = (p.seg_cols > 0) ? (n0 / p.seg_cols) : 0;
@@ -377,7 +427,13 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           }
           if (p.dbg & 1) continue;
           if (!trans) {
-            store_chunk_coalesced(o, stage_addr, lane, m32, obase, ldo, seg_col0 + c, nvalid);
+            if (p.tma_store) {
+              store_chunk_tma(o, stage_addr + tma_buf * 2048u, lane, &p.tmO[seg], p.taps > 1, seg_col0 + c,
+                              tc1, tc2, tc3);
+              tma_buf ^= 1u;
+            } else {
+              store_chunk_coalesced(o, stage_addr, lane, m32, obase, ldo, seg_col0 + c, nvalid);
+            }
           } else if (m >= 0) {
             // per-image transposed store: lanes hold consecutive rows -> 64-byte runs per column
             const long long img = m / p.trans_rows;
@@ -394,6 +450,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (p.tma_store && lane == 0) bulk_wait<0>();
   }
 
   tc_fence_before();
@@ -588,6 +645,42 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
     uint64_t str[2] = {0, static_cast<uint64_t>(a->ldb) * 2};
     uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
     if (encode_tmap_f16(&p.tmB, a->b, 2, dims, str, box)) return -1;
+  }
+
+  {
+    static int tma_store = -1;
+    if (tma_store < 0) {
+      const char* e = getenv("MDK_GEMM_TMA_STORE");
+      tma_store = e ? atoi(e) : 0;
+    }
+    p.tma_store = tma_store;
+  }
+  if (p.tma_store) {
+    const int segw = a->seg_cols > 0 ? a->seg_cols : ncols_out;
+    uint32_t obox4[4] = {32, 1, 1, 1};
+    if (a->conv_taps == 9) {
+      p.sbw = p.bw;
+      p.sbh = p.bh < 32 / p.bw ? p.bh : 32 / p.bw;
+      p.sbn = 32 / (p.sbw * p.sbh);
+      obox4[1] = static_cast<uint32_t>(p.sbw);
+      obox4[2] = static_cast<uint32_t>(p.sbh);
+      obox4[3] = static_cast<uint32_t>(p.sbn);
+    }
+    for (int s = 0; s < nseg; ++s) {
+      if (a->out_trans[s]) continue;
+      const uint64_t ld = static_cast<uint64_t>(a->ldo[s]);
+      if (a->conv_taps == 9) {
+        uint64_t dims[4] = {static_cast<uint64_t>(segw), static_cast<uint64_t>(a->w),
+                            static_cast<uint64_t>(a->h), static_cast<uint64_t>(a->nimg)};
+        uint64_t str[4] = {0, ld * 2, ld * 2 * a->w, ld * 2 * a->w * a->h};
+        if (encode_tmap_f16(&p.tmO[s], a->out[s], 4, dims, str, obox4, 64)) return -1;
+      } else {
+        uint64_t dims[2] = {static_cast<uint64_t>(segw), static_cast<uint64_t>(a->m)};
+        uint64_t str[2] = {0, ld * 2};
+        uint32_t obox[2] = {32, 32};
+        if (encode_tmap_f16(&p.tmO[s], a->out[s], 2, dims, str, obox, 64)) return -1;
+      }
+    }
   }
 
   switch (bn) {

@@ -38,7 +38,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 int encode_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box) {
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -53,7 +53,11 @@ int encode_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t
   }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                   gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                        : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return set_error(

@@ -37,6 +37,6 @@ inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relax
 // Encode a tiled fp16 tensor map (rank 2..5). dims/strides innermost first; strides in BYTES for
 // dims 1..rank-1 (dim 0 is dense). 128-byte swizzle, zero fill out of bounds.
 int encode_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box);
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
 }  // namespace mdk

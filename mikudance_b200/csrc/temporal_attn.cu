@@ -178,9 +178,9 @@ struct TattnTileParams {
   __half* out;
   long long ld, out_ld;
   int nb, f, npix, heads, d, C;
-  int pg;        // pixels per CTA
-  int rs;        // smem row stride in halves (3C + 8)
-  int qpw;
+  int hg;        // heads per CTA (one warp each); the CTA stages only their q|k|v column segments
+  int seg;       // hg * d: columns of one segment
+  int rs;        // smem row stride in halves (3*seg + 8)
   float scale_log2;
 };
 
@@ -215,35 +215,37 @@ __global__ void __launch_bounds__(256) temporal_attn_tile_kernel(const TattnTile
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __half* sm = reinterpret_cast<__half*>(smem_raw);
   constexpr int FP = 16 * MT;
-  const int groups_per_b = (p.npix + p.pg - 1) / p.pg;
-  const int b = blockIdx.x / groups_per_b;
-  const int px0 = (blockIdx.x % groups_per_b) * p.pg;
-  const int npx = min(p.pg, p.npix - px0);
-  const int rowv = (3 * p.C) >> 3;  // 16-byte vectors per row
-  // ---- coalesced load: for each frame the npx pixel rows are one contiguous run ----
-  for (int j = 0; j < FP; ++j) {
-    const __half* src = p.qkv + ((static_cast<long long>(b) * p.f + j) * p.npix + px0) * p.ld;
-    for (int i = threadIdx.x; i < npx * rowv; i += blockDim.x) {
-      const int px = i / rowv, v = i % rowv;
-      uint4 val = make_uint4(0, 0, 0, 0);                 // frames >= f: zero rows (P is 0 there)
-      if (j < p.f) val = *reinterpret_cast<const uint4*>(src + static_cast<long long>(px) * p.ld + v * 8);
-      *reinterpret_cast<uint4*>(sm + (static_cast<long long>(px) * FP + j) * p.rs + v * 8) = val;
-    }
+  // CTA = (batch entry, pixel, head group): small CTAs (31 KB of smem at any level) so that 6-7 of
+  // them overlap their load / compute / store phases on one SM
+  const int ngroups = p.heads / p.hg;
+  const int hgi = blockIdx.x % ngroups;
+  const long long bp = blockIdx.x / ngroups;
+  const int px = static_cast<int>(bp % p.npix);
+  const int b = static_cast<int>(bp / p.npix);
+  const int segv = p.seg >> 3;           // 16-byte vectors per segment
+  const int col0 = hgi * p.seg;          // first channel of this head group
+  // ---- load the q | k | v segments of every frame (zero rows for padded frames) ----
+  for (int i = threadIdx.x; i < FP * 3 * segv; i += blockDim.x) {
+    const int v = i % segv;
+    const int which = (i / segv) % 3;
+    const int j = i / (3 * segv);
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (j < p.f)
+      val = *reinterpret_cast<const uint4*>(
+          p.qkv + ((static_cast<long long>(b) * p.f + j) * p.npix + px) * p.ld + which * p.C + col0 + v * 8);
+    *reinterpret_cast<uint4*>(sm + static_cast<long long>(j) * p.rs + which * p.seg + v * 8) = val;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int nprob = npx * p.heads;
   const int ksteps = (p.d + 15) >> 4;
   const bool half_last = (p.d & 15) != 0;  // d % 16 == 8: upper half of the last K step is padding
   const int ntile_o = p.d >> 3;
-  const uint32_t sm_base = smem_u32(sm);
   const uint32_t rsb = static_cast<uint32_t>(p.rs) * 2u;  // row stride in bytes
-  for (int pr = warp; pr < nprob; pr += warps) {
-    const int px = pr / p.heads, h = pr % p.heads;
-    const uint32_t qb = sm_base + (static_cast<uint32_t>(px) * FP * p.rs + h * p.d) * 2u;
-    const uint32_t kb = qb + static_cast<uint32_t>(p.C) * 2u;
-    const uint32_t vb = qb + static_cast<uint32_t>(p.C) * 4u;
+  if (warp < p.hg) {
+    const uint32_t qb = smem_u32(sm) + static_cast<uint32_t>(warp * p.d) * 2u;
+    const uint32_t kb = qb + static_cast<uint32_t>(p.seg) * 2u;
+    const uint32_t vb = qb + static_cast<uint32_t>(p.seg) * 4u;
     // ---- S = Q K^T ----
     float sacc[MT][2 * MT][4];
 #pragma unroll
@@ -352,15 +354,12 @@ __global__ void __launch_bounds__(256) temporal_attn_tile_kernel(const TattnTile
     }
   }
   __syncthreads();
-  // ---- coalesced store of the O rows (first C columns of every staged row) ----
-  const int outv = p.C >> 3;
-  for (int j = 0; j < p.f; ++j) {
-    __half* dst = p.out + ((static_cast<long long>(b) * p.f + j) * p.npix + px0) * p.out_ld;
-    for (int i = threadIdx.x; i < npx * outv; i += blockDim.x) {
-      const int px = i / outv, v = i % outv;
-      *reinterpret_cast<uint4*>(dst + static_cast<long long>(px) * p.out_ld + v * 8) =
-          *reinterpret_cast<const uint4*>(sm + (static_cast<long long>(px) * FP + j) * p.rs + v * 8);
-    }
+  // ---- store the O segment of every frame (first `seg` columns of every staged row) ----
+  for (int i = threadIdx.x; i < p.f * segv; i += blockDim.x) {
+    const int v = i % segv, j = i / segv;
+    *reinterpret_cast<uint4*>(p.out + ((static_cast<long long>(b) * p.f + j) * p.npix + px) * p.out_ld +
+                              col0 + v * 8) =
+        *reinterpret_cast<const uint4*>(sm + static_cast<long long>(j) * p.rs + v * 8);
   }
 }
 
@@ -385,10 +384,16 @@ extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void
     const bool fused = a->q == a->kv && a->q_off == 0 && a->k_off == C && a->v_off == 2 * C &&
                        a->q_ld == a->kv_ld && a->q_ld >= 3 * C && a->f_q == a->f_kv &&
                        f_kv_rank == a->f_kv && a->f_q_offset == 0;
-    const int rs = 3 * C + 8;
+    // heads per CTA: keep one q/k/v segment around 640 B (good coalescing, ~31 KB of smem per CTA)
+    int hg = a->heads;
+    while (hg > 1 && hg % 2 == 0 && (hg / 2) * a->d >= 320) hg /= 2;
+    if (hg > 8) hg = 8;
+    while (a->heads % hg != 0) --hg;
+    const int seg = hg * a->d;
+    const int rs = 3 * seg + 8;
     const int fp = a->f_q <= 16 ? 16 : 32;
-    const size_t per_px = static_cast<size_t>(fp) * rs * sizeof(__half);
-    if (fused && a->pe_q == nullptr && per_px <= 200 * 1024) {
+    const size_t smem = static_cast<size_t>(fp) * rs * sizeof(__half);
+    if (fused && a->pe_q == nullptr && smem <= 200 * 1024) {
       TattnTileParams t;
       t.qkv = static_cast<const __half*>(a->q);
       t.pe_q = nullptr;
@@ -401,18 +406,10 @@ extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void
       t.heads = a->heads;
       t.d = a->d;
       t.C = C;
+      t.hg = hg;
+      t.seg = seg;
       t.rs = rs;
-      int qpw = 1;
-      while (qpw < a->f_q) qpw *= 2;
-      t.qpw = qpw;
       t.scale_log2 = a->scale * 1.4426950408889634f;
-      int pg = static_cast<int>((96 * 1024) / per_px);   // two CTAs per SM when possible
-      if (pg < 1) pg = 1;
-      if (pg > a->npix) pg = a->npix;
-      if (pg > 8) pg = 8;
-      t.pg = pg;
-      const size_t smem = per_px * pg;
-      const int groups = (a->npix + pg - 1) / pg;
       static bool tile_attr = false;
       if (!tile_attr) {
         MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_tile_kernel<1>,
@@ -421,11 +418,13 @@ extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         tile_attr = true;
       }
-      const unsigned grid = static_cast<unsigned>(a->nb) * groups;
+      const long long grid = static_cast<long long>(a->nb) * a->npix * (a->heads / hg);
+      MDK_REQUIRE(grid < (1ll << 31), "mdk_temporal_attn_f16: grid too large");
+      const int threads = 32 * hg < 64 ? 64 : 32 * hg;
       if (a->f_q <= 16)
-        temporal_attn_tile_kernel<1><<<grid, 256, smem, stream>>>(t);
+        temporal_attn_tile_kernel<1><<<static_cast<unsigned>(grid), threads, smem, stream>>>(t);
       else
-        temporal_attn_tile_kernel<2><<<grid, 256, smem, stream>>>(t);
+        temporal_attn_tile_kernel<2><<<static_cast<unsigned>(grid), threads, smem, stream>>>(t);
       count_launch();
       MDK_CHECK_CUDA(cudaGetLastError());
       return 0;
