@@ -303,7 +303,7 @@ def main():
 
     # ---- per-kernel profile of one eager step (CUDA events around every launch) ----
     peaks = measured_peaks()
-    roofline, kernels = None, None
+    roofline, kernels, shapes = None, None, None
     if not args.skip_profile:
         prof = ops.Profiler()
         ops.set_profiler(prof)
@@ -312,6 +312,7 @@ def main():
         torch.cuda.synchronize(dev)
         ops.set_profiler(None)
         kernels = prof.summary()
+        shapes = prof.shapes(24)
         g = kernels.get("gemm_tc")
         if g and g["ms"] > 0:
             ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
@@ -350,7 +351,7 @@ def main():
                     roofline_step=dict(bound="tensor", algorithmic_tflop_per_step=step_tflop,
                                        achieved=step_ach, peak=peaks["tflops_sustained"], unit="TFLOP/s",
                                        frac=(step_ach / peaks["tflops_sustained"]) if step_ach else None),
-                    kernels=kernels, cpu_baseline=cpu)
+                    kernels=kernels, top_shapes=shapes, cpu_baseline=cpu)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -61,14 +61,15 @@ struct GemmCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int STAGES = (BN >= 192) ? 4 : (BN >= 160 ? 5 : 6);
-  static constexpr int EPI_STAGING = EPI_WARPS * 2 * 32 * 64;  // per epilogue warp: 2 x (32 rows x 32 fp16)
+  static constexpr int EPI_STAGING = EPI_WARPS * 2 * 32 * 64;  // per epilogue warp: output + residual sub-tile
   static constexpr int TMEM_COLS = (2 * BN <= 32)    ? 32
                                    : (2 * BN <= 64)  ? 64
                                    : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256
                                                      : 512;
-  static constexpr int SMEM_BYTES =
-      STAGES * STAGE_BYTES + EPI_STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BIAS = EPI_WARPS * 256;  // per epilogue warp: bias of the current chunk(s)
+  // dynamic shared memory is declared __align__(1024) (checked at run time): no alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING + EPI_BIAS + 256 /*barriers*/;
 };
 
 // GELU with the exact (erf) formulation of diffusers' GEGLU.  erf by Abramowitz-Stegun 7.1.26
@@ -119,12 +120,14 @@ __device__ __forceinline__ void store_chunk_coalesced(const float (&o)[32], uint
   __syncwarp();
 }
 
-// TMA-store variant: the sub-tile goes to a (double-buffered) staging buffer in the 64B-swizzled
-// layout and one elected lane issues an asynchronous bulk tensor store; bounds are clipped by TMA.
+// TMA-store variant: the sub-tile goes to the warp's staging buffer in the 64B-swizzled layout and
+// one elected lane issues an asynchronous bulk tensor store; bounds are clipped by TMA.  The wait for
+// the previous store sits at the top of the next chunk's store, i.e. behind that chunk's TMEM load,
+// bias / residual adds and conversion.
 __device__ __forceinline__ void store_chunk_tma(const float (&o)[32], uint32_t buf_addr, int lane,
                                                 const CUtensorMap* tm, bool conv, int c0, int c1, int c2,
                                                 int c3) {
-  if (lane == 0) bulk_wait_read<1>();  // the store that last read this buffer has drained
+  if (lane == 0) bulk_wait_read<0>();  // the previous store has finished reading the staging buffer
   __syncwarp();
   const uint32_t my = buf_addr + static_cast<uint32_t>(lane) * 64u;
   const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
@@ -150,14 +153,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment required by the 128B swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;  // 1024-byte alignment required by the 128B swizzle atoms
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("mdk gemm: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
   uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_STAGING);
+  uint8_t* smem_bias = smem_epi + Cfg::EPI_STAGING;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + Cfg::EPI_BIAS);
   uint64_t* full_bar = bars;                     // [STAGES]
   uint64_t* empty_bar = bars + STAGES;           // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]
@@ -280,7 +286,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     const int cgroup = (warp - 2) >> 2;     // 0/1: which half of the 32-column chunks this warp takes
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t stage_addr = smem_u32(smem_epi) + static_cast<uint32_t>(warp - 2) * 4096u;
-    uint32_t tma_buf = 0;  // which of the warp's two staging buffers the next TMA store uses
+    const uint32_t bias_addr = smem_u32(smem_bias) + static_cast<uint32_t>(warp - 2) * 256u;
     uint32_t acc_phase[2] = {0, 0};
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -321,9 +327,6 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       if (p.row_bias != nullptr && m >= 0)
         rb = p.row_bias + static_cast<long long>((m / p.row_div) % p.row_mod) * p.N;
 
-      mbar_wait(&tfull_bar[acc], acc_phase[acc]);
-      acc_phase[acc] ^= 1u;
-      tc_fence_after();
       const uint32_t t_acc =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
@@ -332,25 +335,40 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         // tile columns [0, BN/2) are values, [BN/2, BN) the matching gates
         constexpr int HALF = BN / 2;
         const int ocol0 = n_tile * HALF;
+        mbar_wait(&tfull_bar[acc], acc_phase[acc]);
+        acc_phase[acc] ^= 1u;
+        tc_fence_after();
         for (int c = cgroup * 32; c < HALF; c += 64) {
           if (n0 + c >= p.N) break;
           uint32_t vh[32], vg[32];
           tmem_ld_x32(t_acc + c, vh);
           tmem_ld_x32(t_acc + HALF + c, vg);
+          // bias of the 32 value and 32 gate columns: one global load per lane, read back as
+          // shared-memory broadcasts
+          if (p.bias) {
+            sts32(bias_addr + static_cast<uint32_t>(lane) * 4u, __float_as_uint(__ldg(p.bias + n0 + c + lane)));
+            sts32(bias_addr + 128u + static_cast<uint32_t>(lane) * 4u,
+                  __float_as_uint(__ldg(p.bias + n0 + HALF + c + lane)));
+          }
+          __syncwarp();
           tmem_wait_ld();
           float o[32];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
             if (p.bias) {
-              bh = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + j4);
-              bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + HALF + c) + j4);
+              uint4 r0, r1;
+              ld_shared_v4(bias_addr + static_cast<uint32_t>(j4) * 16u, r0);
+              ld_shared_v4(bias_addr + 128u + static_cast<uint32_t>(j4) * 16u, r1);
+              bh = make_float4(__uint_as_float(r0.x), __uint_as_float(r0.y), __uint_as_float(r0.z), __uint_as_float(r0.w));
+              bg = make_float4(__uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z), __uint_as_float(r1.w));
             }
             o[j4 * 4 + 0] = (__uint_as_float(vh[j4 * 4 + 0]) + bh.x) * gelu_erf(__uint_as_float(vg[j4 * 4 + 0]) + bg.x);
             o[j4 * 4 + 1] = (__uint_as_float(vh[j4 * 4 + 1]) + bh.y) * gelu_erf(__uint_as_float(vg[j4 * 4 + 1]) + bg.y);
             o[j4 * 4 + 2] = (__uint_as_float(vh[j4 * 4 + 2]) + bh.z) * gelu_erf(__uint_as_float(vg[j4 * 4 + 2]) + bg.z);
             o[j4 * 4 + 3] = (__uint_as_float(vh[j4 * 4 + 3]) + bh.w) * gelu_erf(__uint_as_float(vg[j4 * 4 + 3]) + bg.w);
           }
+          __syncwarp();
           if (p.residual && m >= 0) {
             const __half* rsrc = p.residual + m * p.ldr + ocol0 + c;
 #pragma unroll
@@ -367,9 +385,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           }
           if (!(p.dbg & 1)) {
             if (p.tma_store) {
-              store_chunk_tma(o, stage_addr + tma_buf * 2048u, lane, &p.tmO[0], p.taps > 1, ocol0 + c, tc1,
-                              tc2, tc3);
-              tma_buf ^= 1u;
+              store_chunk_tma(o, stage_addr, lane, &p.tmO[0], p.taps > 1, ocol0 + c, tc1, tc2, tc3);
             } else {
               store_chunk_coalesced(o, stage_addr, lane, m32, p.out[0], p.ldo[0], ocol0 + c, 32);
             }
@@ -381,35 +397,94 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         __half* obase = p.out[seg];
         const long long ldo = p.ldo[seg];
         const bool trans = p.out_trans[seg] != 0;
+        // Everything the epilogue needs besides the accumulator is fetched ahead of use and handed
+        // over through warp-private shared memory: the chunk's 32 bias values (one per lane, read
+        // back as broadcasts) and the residual sub-tile (coalesced 64-byte row segments, read back
+        // as this lane's own row).  ncu showed the epilogue stalled on exactly these global loads.
+        const bool res_staged = p.residual != nullptr;
+        const uint32_t res_buf = stage_addr + 2048u;
         uint32_t v[32];
+        float bv = 0.f;
+        uint4 rres[4];
         int c = cgroup * 32;
-        if (n0 + c < p.N && c < BN) tmem_ld_x32(t_acc + c, v);
+        auto prefetch_aux = [&](int cc) {
+          const int col = n0 + cc;
+          bv = (p.bias != nullptr && col + lane < p.N) ? __ldg(p.bias + col + lane) : 0.f;
+          if (res_staged) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int t = i * 32 + lane;
+              const int row = t >> 2, q = t & 3;
+              const int m_r = __shfl_sync(0xffffffffu, static_cast<int>(m), row);
+              rres[i] = (m_r >= 0 && col + q * 8 < p.N)
+                            ? *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(m_r) * p.ldr +
+                                                              col + q * 8)
+                            : make_uint4(0, 0, 0, 0);
+            }
+          }
+        };
+        const bool any_chunk = c < BN && n0 + c < p.N;
+        if (any_chunk) prefetch_aux(c);          // overlaps the wait for the accumulator
+        mbar_wait(&tfull_bar[acc], acc_phase[acc]);
+        acc_phase[acc] ^= 1u;
+        tc_fence_after();
+        if (any_chunk) tmem_ld_x32(t_acc + c, v);
         for (; c < BN; c += 64) {
           if (n0 + c >= p.N) break;  // warp-uniform
           tmem_wait_ld();
           float acc_f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc_f[j] = __uint_as_float(v[j]);
+          sts32(bias_addr + static_cast<uint32_t>(lane) * 4u, __float_as_uint(bv));
+          if (res_staged) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int t = i * 32 + lane;
+              const uint32_t row = static_cast<uint32_t>(t >> 2), q = static_cast<uint32_t>(t & 3);
+              st_shared_v4(res_buf + row * 64u + ((q ^ ((row >> 1) & 3u)) << 4), rres[i].x, rres[i].y,
+                           rres[i].z, rres[i].w);
+            }
+          }
+          __syncwarp();
           // prefetch this warp's next chunk while the current one is converted and stored
-          if (c + 64 < BN && n0 + c + 64 < p.N) tmem_ld_x32(t_acc + c + 64, v);
+          const bool has_next = c + 64 < BN && n0 + c + 64 < p.N;
+          if (has_next) {
+            tmem_ld_x32(t_acc + c + 64, v);
+            prefetch_aux(c + 64);
+          }
           const int nvalid = min(32, p.N - (n0 + c));   // multiple of 8
           float o[32];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j4 * 4 < nvalid) {
-              if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + j4);
-              if (rb) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(rb + n0 + c) + j4);
-                b.x += r.x; b.y += r.y; b.z += r.z; b.w += r.w;
-              }
+            uint4 braw;
+            ld_shared_v4(bias_addr + static_cast<uint32_t>(j4) * 16u, braw);
+            float4 b = make_float4(__uint_as_float(braw.x), __uint_as_float(braw.y), __uint_as_float(braw.z),
+                                   __uint_as_float(braw.w));
+            if (rb && j4 * 4 < nvalid) {
+              const float4 r = __ldg(reinterpret_cast<const float4*>(rb + n0 + c) + j4);
+              b.x += r.x; b.y += r.y; b.z += r.z; b.w += r.w;
             }
             o[j4 * 4 + 0] = acc_f[j4 * 4 + 0] + b.x;
             o[j4 * 4 + 1] = acc_f[j4 * 4 + 1] + b.y;
             o[j4 * 4 + 2] = acc_f[j4 * 4 + 2] + b.z;
             o[j4 * 4 + 3] = acc_f[j4 * 4 + 3] + b.w;
           }
-          if (p.residual && m >= 0) {
+          if (res_staged) {
+            const uint32_t myrow = res_buf + static_cast<uint32_t>(lane) * 64u;
+            const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+              uint4 rv;
+              ld_shared_v4(myrow + ((q ^ sw) << 4), rv);
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __half22float2(rh[e]);
+                o[q * 8 + 2 * e] += f.x;
+                o[q * 8 + 2 * e + 1] += f.y;
+              }
+            }
+          } else if (p.residual && m >= 0) {
             const __half* rsrc = p.residual + m * p.ldr + n0 + c;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -428,9 +503,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           if (p.dbg & 1) continue;
           if (!trans) {
             if (p.tma_store) {
-              store_chunk_tma(o, stage_addr + tma_buf * 2048u, lane, &p.tmO[seg], p.taps > 1, seg_col0 + c,
-                              tc1, tc2, tc3);
-              tma_buf ^= 1u;
+              store_chunk_tma(o, stage_addr, lane, &p.tmO[seg], p.taps > 1, seg_col0 + c, tc1, tc2, tc3);
             } else {
               store_chunk_coalesced(o, stage_addr, lane, m32, obase, ldo, seg_col0 + c, nvalid);
             }
@@ -651,7 +724,7 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
     static int tma_store = -1;
     if (tma_store < 0) {
       const char* e = getenv("MDK_GEMM_TMA_STORE");
-      tma_store = e ? atoi(e) : 0;
+      tma_store = e ? atoi(e) : 1;   // default: TMA-store epilogue (MDK_GEMM_TMA_STORE=0 selects st.global)
     }
     p.tma_store = tma_store;
   }

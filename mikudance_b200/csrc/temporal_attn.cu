@@ -197,14 +197,6 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t& r0, u
                : "=r"(r0), "=r"(r1)
                : "r"(addr));
 }
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory");
-}
 
 // One warp per (pixel, head) problem.  The tiny GEMMs run on the legacy mma.sync path on purpose:
 // a 16 x 16 x 40 problem cannot fill a tcgen05 128-row tile, the kernel is HBM-bound, and

@@ -27,7 +27,7 @@ class Profiler:
         torch.cuda.synchronize()
         out = {}
         for kind, flops, nbytes, e0, e1 in self.records:
-            d = out.setdefault(kind, dict(n=0, ms=0.0, flops=0.0, bytes=0.0))
+            d = out.setdefault(kind.split(":")[0], dict(n=0, ms=0.0, flops=0.0, bytes=0.0))
             d["n"] += 1
             d["ms"] += e0.elapsed_time(e1)
             d["flops"] += flops
@@ -37,6 +37,20 @@ class Profiler:
                 d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12
                 d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
         return out
+
+
+    def shapes(self, top=16):
+        """per-shape breakdown (kind strings carry the problem shape after the first ':')"""
+        torch.cuda.synchronize()
+        out = {}
+        for kind, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(kind, dict(n=0, ms=0.0, flops=0.0))
+            d["n"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+        rows = sorted(out.items(), key=lambda kv: -kv[1]["ms"])[:top]
+        return [dict(shape=k, n=v["n"], ms=round(v["ms"], 3),
+                     tflops=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] > 0 else 0.0) for k, v in rows]
 
 
 _PROF: Optional[Profiler] = None
@@ -134,7 +148,13 @@ def gemm(a0: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None
                 args.ldo[s] = o.stride(0)
         ret = outs
     ktot = (9 if conv is not None else 1) * (k0 + k1)
-    _run("gemm_tc", 2.0 * M * N * ktot, 2.0 * (M * (k0 + k1) + N * ktot + M * n_out * (2 if residual is not None else 1)),
+    tag = "gemm_tc"
+    if _PROF is not None:
+        tag = (f"gemm_tc:{'conv' if conv is not None else 'lin'} M={M} N={N} K={ktot}"
+               f"{' bias' if bias is not None else ''}{' rowbias' if row_bias is not None else ''}"
+               f"{' res' if residual is not None else ''}{' geglu' if geglu else ''}"
+               f"{' seg' + str(len(outs)) if outs is not None else ''}{' T' if (outs is not None and any(trans)) else ''}")
+    _run(tag, 2.0 * M * N * ktot, 2.0 * (M * (k0 + k1) + N * ktot + M * n_out * (2 if residual is not None else 1)),
          lambda: lib.mdk_gemm_f16(get_ctx(dev), C.byref(args), cur_stream(dev)), "mdk_gemm_f16")
     return ret
 
@@ -153,7 +173,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, nimg: int, 
     a.nimg, a.nkv, a.kv_div = nimg, vt.shape[0], kv_div
     a.lq, a.lkv, a.heads, a.d = lq, lkv, heads, d
     a.scale = scale if scale is not None else 1.0 / math.sqrt(d)
-    _run("attn_tc", 4.0 * nimg * heads * lq * lkv * d, 2.0 * heads * d * (2 * nimg * lq + 2 * vt.shape[0] * lkv),
+    _run(f"attn_tc:L={lq}x{lkv} d={d} n={nimg}" if _PROF is not None else "attn_tc",
+         4.0 * nimg * heads * lq * lkv * d, 2.0 * heads * d * (2 * nimg * lq + 2 * vt.shape[0] * lkv),
          lambda: load_library().mdk_attn_fwd_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
          "mdk_attn_fwd_f16")
     return out

@@ -2,9 +2,8 @@
 mkdir -p gpurun_out
 make -j8 >/dev/null 2>&1 || echo "MAKE FAILED"
 export PYTHONUNBUFFERED=1
-( timeout 600 python -m pytest tests -m gpu -q -k "kernels or tiny" 2>&1 | tail -8 ) | tee gpurun_out/pytest_gpu.log
-( timeout 400 python tests/gpu_diag.py ncu_gemm2 perf_gemm_small perf_attn perf_misc 2>&1 | grep -E "perf|==" ) | tee gpurun_out/perf_micro.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 4 -c 2 -o gpurun_out/prof_gemm2 python tests/gpu_diag.py ncu_gemm2 > gpurun_out/ncu_gemm2.log 2>&1; tail -2 gpurun_out/ncu_gemm2.log
+( timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -12 ) | tee gpurun_out/pytest_gpu.log
+( timeout 400 python tests/gpu_diag.py ncu_gemm2 perf_gemm_small perf_gemm 2>&1 | grep -E "perf|==" ) | tee gpurun_out/perf_micro.log
 ( timeout 900 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline 2> gpurun_out/bench_stderr.log | tee gpurun_out/bench.json ) | cut -c1-300
 tail -5 gpurun_out/bench_stderr.log
 ls -la gpurun_out
