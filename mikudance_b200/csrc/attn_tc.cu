@@ -13,6 +13,8 @@
 // K/V projection GEMM), so P V needs no MN-major operand.
 //
 // Algorithmic FLOPs per launch: 4 * nimg * heads * lq * lkv * d.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 #include "../../include/mdk.h"
@@ -63,13 +65,16 @@ struct AttnCfg {
   static constexpr int SMEM_BYTES = Q_BYTES + KST * (K_STAGE + V_STAGE) + P_BYTES + 256;
   // S (128 x BKV fp32, single buffer: it is drained into registers at the start of each softmax
   // step) at column 0, O (128 x 64*NCH fp32) at column 128
-  static constexpr uint32_t S_COL = 0, O_COL = 128;
-  static constexpr uint32_t TMEM_COLS = (128 + 64 * NCH <= 256) ? 256 : 512;
-  static constexpr int CTAS_PER_SM = (NCH == 1) ? 2 : 1;
+  static constexpr uint32_t S_COL = 0, O_COL = BKV;
+  static constexpr uint32_t TMEM_COLS = (BKV + 64 * NCH <= 128) ? 128 : (BKV + 64 * NCH <= 256) ? 256 : 512;
+  // head_dim <= 64: 3 CTAs/SM with 64-key tiles (64 KB smem, 128 TMEM columns, <= 112 registers) or
+  // 2 CTAs/SM with 128-key tiles.  The softmax warps are latency-bound (ncu: MUFU 62 %, issue 45 % at
+  // 2 CTAs/SM), so more independent CTAs per SM is what raises the MUFU utilisation.
+  static constexpr int CTAS_PER_SM = (NCH == 1) ? (BKV == 64 ? 3 : 2) : 1;
 };
 
 template <int NCH, int BKV, int KST>
-__global__ void __launch_bounds__(ATT_THREADS, (NCH == 1) ? 2 : 1)
+__global__ void __launch_bounds__(ATT_THREADS, (NCH == 1) ? (BKV == 64 ? 3 : 2) : 1)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<NCH, BKV, KST>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -414,7 +419,15 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
   p.dn = p.dk16 * 16;
   p.kv_div = a->kv_div;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  if (a->d <= 64) return launch_attn<1, 128, 2>(ctx, p, a, stream);  // 2 CTAs per SM
+  if (a->d <= 64) {
+    static int bkv = -1;
+    if (bkv < 0) {
+      const char* e = getenv("MDK_ATTN_BKV");
+      bkv = e ? atoi(e) : 64;
+    }
+    if (bkv == 128) return launch_attn<1, 128, 2>(ctx, p, a, stream);  // 2 CTAs per SM
+    return launch_attn<1, 64, 2>(ctx, p, a, stream);                     // 3 CTAs per SM
+  }
   if (a->d <= 128) return launch_attn<2, 128, 2>(ctx, p, a, stream);
   return launch_attn<3, 64, 2>(ctx, p, a, stream);
 }

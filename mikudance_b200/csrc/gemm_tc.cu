@@ -323,9 +323,18 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       } else {
         tc1 = m_tile * BM + quarter * 32;
       }
-      const float* rb = nullptr;
-      if (p.row_bias != nullptr && m >= 0)
-        rb = p.row_bias + static_cast<long long>((m / p.row_div) % p.row_mod) * p.N;
+      // per-row bias (temporal PE): when a warp's 32 rows share one group (row_div % 32 == 0 in plain
+      // GEMM mode) it is folded into the staged per-column bias; otherwise every thread loads its own
+      const float* rb = nullptr;       // per-thread path
+      const float* rb_warp = nullptr;  // warp-uniform path
+      if (p.row_bias != nullptr) {
+        if (p.taps == 1 && (p.row_div & 31) == 0) {
+          const long long m_first = static_cast<long long>(m_tile) * BM + quarter * 32;
+          if (m_first < p.M) rb_warp = p.row_bias + static_cast<long long>((m_first / p.row_div) % p.row_mod) * p.N;
+        } else if (m >= 0) {
+          rb = p.row_bias + static_cast<long long>((m / p.row_div) % p.row_mod) * p.N;
+        }
+      }
 
       const uint32_t t_acc =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
@@ -410,6 +419,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         auto prefetch_aux = [&](int cc) {
           const int col = n0 + cc;
           bv = (p.bias != nullptr && col + lane < p.N) ? __ldg(p.bias + col + lane) : 0.f;
+          if (rb_warp != nullptr && col + lane < p.N) bv += __ldg(rb_warp + col + lane);
           if (res_staged) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
