@@ -547,16 +547,22 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int pick_bn(int n, int seg_cols, int nseg) {
+// Tile width: among the widths that divide the segment width, minimise (waves on this GPU) x
+// (tile width ~ tile time) with the padded columns charged in full; ties go to the wider tile
+// (fewer A re-reads from L2).  E.g. M=4608, N=1280: 128x256 tiles need 2 waves of 180 tiles
+// (cost 512) while 128x160 tiles fill 1.95 waves of 288 (cost 320).
+static int pick_bn(int n, int seg_cols, int nseg, int m_tiles, int num_sms) {
   const int cands[] = {256, 192, 160, 128, 64, 32};
   int best = 0;
-  long long best_pad = 0;
+  long long best_cost = 0;
   for (int bn : cands) {
     if (nseg > 1 && (seg_cols % bn) != 0) continue;
-    long long pad = static_cast<long long>((n + bn - 1) / bn) * bn;
-    if (best == 0 || pad < best_pad) {
+    const long long n_tiles = (n + bn - 1) / bn;
+    const long long waves = (n_tiles * m_tiles + num_sms - 1) / num_sms;
+    const long long cost = waves * (bn < 128 ? 128 : bn);  // narrow tiles do not get cheaper: smem-bound MMA
+    if (best == 0 || cost < best_cost) {
       best = bn;
-      best_pad = pad;
+      best_cost = cost;
     }
   }
   return best;
@@ -671,7 +677,8 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
     bn = 256;
     MDK_REQUIRE(a->n % 256 == 0, "mdk_gemm_f16: geglu needs n %% 256 == 0 (n=%d)", a->n);
   } else {
-    bn = pick_bn(a->n, a->seg_cols, nseg);
+    int m_tiles_est = (a->m + BM - 1) / BM;   // (conv tiles are also 128 pixels)
+    bn = pick_bn(a->n, a->seg_cols, nseg, m_tiles_est, ctx->num_sms);
     MDK_REQUIRE(bn > 0, "mdk_gemm_f16: no tile width divides seg_cols=%d", a->seg_cols);
   }
   p.n_tiles = (a->n + bn - 1) / bn;
