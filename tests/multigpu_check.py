@@ -46,8 +46,10 @@ def main():
             return synth.synthetic_banks(cfg, 2 * len(wdw), h, w, seed=300 + wdw[0])
 
         res = {}
-        for name, pg, graph in (("single", None, True), ("sharded", dist.group.WORLD, True),
-                                ("sharded-eager", dist.group.WORLD, False)):
+        for name, pg, graph, mode in (("single", None, True, "a2a"), ("sharded", dist.group.WORLD, True, "a2a"),
+                                      ("sharded-eager", dist.group.WORLD, False, "a2a"),
+                                      ("sharded-allgather", dist.group.WORLD, True, "allgather")):
+            m.engine().shard_mode = mode
             loop = DenoiseLoop(m, DDIMScheduler(**kw), guidance_scale=3.5, context_frames=ctxf,
                                context_stride=1, context_overlap=ov, process_group=pg, use_cuda_graph=graph)
             loop.prepare(lat.to(dev).contiguous().clone(), ctx, 3, banks_for_window)
@@ -55,14 +57,15 @@ def main():
             torch.cuda.synchronize()
             dist.barrier()
         rel = ((res["sharded"] - res["single"]).norm() / res["single"].norm()).item()
+        rel_ag = ((res["sharded-allgather"] - res["single"]).norm() / res["single"].norm()).item()
         same = torch.equal(res["sharded"], res["sharded-eager"])
-        flag = torch.tensor([1.0 if (rel < 3e-3 and same) else 0.0], device=dev)
+        flag = torch.tensor([1.0 if (rel < 3e-3 and rel_ag < 3e-3 and same) else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # every rank must agree (latents are replicated)
         ok &= bool(flag.item() > 0.5)
         if rank == 0:
-            print(f"F={F_} ctx={ctxf}: windows={[len(x) for x in loop.windows]} sharded-vs-single rel_l2={rel:.3e} "
+            print(f"F={F_} ctx={ctxf}: windows={[len(x) for x in loop.windows]} a2a-vs-single rel_l2={rel:.3e} allgather-vs-single rel_l2={rel_ag:.3e} "
                   f"graph==eager {same}", flush=True)
-            ok &= rel < 3e-3 and same
+            ok &= rel < 3e-3 and rel_ag < 3e-3 and same
     if rank == 0:
         print("MULTIGPU", "PASS" if ok else "FAIL", flush=True)
     dist.destroy_process_group()
