@@ -80,6 +80,11 @@ typedef struct {
   int32_t out_trans[3];
   int32_t trans_rows;
   int64_t trans_ld;
+  /* transposed segments only: when trans_head_dp > trans_head_d > 0 the seg_cols channels are taken as
+   * heads of trans_head_d channels and head h is written to rows [h*trans_head_dp, h*trans_head_dp +
+   * trans_head_d) of an image (padded per-head V^T: the pad rows belong to the caller, e.g. a row of
+   * ones that makes the attention kernel's P.V MMA also produce the softmax row sums). */
+  int32_t trans_head_d, trans_head_dp;
 } mdk_gemm_args;
 
 int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* args, void* stream);
@@ -95,7 +100,10 @@ int mdk_gemm_geglu_block(void);
  *
  * q   : [nimg, lq, heads*d] fp16 (row stride ldq elements)
  * k   : [nkv , lkv, heads*d] fp16 (row stride ldk)
- * vt  : [nkv , heads*d, ldvt] fp16 — V transposed per image (row = channel, col = kv index)
+ * vt  : [nkv , heads*vt_head_rows, ldvt] fp16 — V transposed per image (row = head*vt_head_rows +
+ *       channel, col = kv index); vt_head_rows = 0 means d.  With vt_ones != 0 (needs d % 16 == 8 and
+ *       vt_head_rows >= d + 8) row d of every head holds ones and the kernel takes the softmax row sums
+ *       from that extra output column of P.V instead of adding them up in the softmax warps.
  * out : [nimg, lq, heads*d] fp16 (row stride ldo)
  * image i attends to kv batch (i / kv_div)   (kv_div = 1: self-attention; = frames per branch
  * for the shared CLIP context). scale = softmax scale (d^-0.5).
@@ -110,6 +118,7 @@ typedef struct {
   int32_t nimg, nkv, kv_div;
   int32_t lq, lkv, heads, d;
   float scale;
+  int32_t vt_head_rows, vt_ones;
 } mdk_attn_args;
 
 int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* args, void* stream);

@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("geglu", c_int32), ("seg_cols", c_int32),
         ("out", c_void_p * 3), ("ldo", c_int64 * 3), ("out_trans", c_int32 * 3),
         ("trans_rows", c_int32), ("trans_ld", c_int64),
+        ("trans_head_d", c_int32), ("trans_head_dp", c_int32),
     ]
 
 
@@ -42,6 +43,7 @@ class AttnArgs(C.Structure):
         ("nimg", c_int32), ("nkv", c_int32), ("kv_div", c_int32),
         ("lq", c_int32), ("lkv", c_int32), ("heads", c_int32), ("d", c_int32),
         ("scale", c_float),
+        ("vt_head_rows", c_int32), ("vt_ones", c_int32),
     ]
 
 

@@ -51,6 +51,7 @@ struct AttnParams {
   int kv_div;
   int n_kv_tiles;
   float scale_log2;
+  int vt_head_rows;  // rows per head in V^T (>= d)
 };
 
 template <int NCH, int BKV, int KST>
@@ -73,7 +74,10 @@ struct AttnCfg {
   static constexpr int CTAS_PER_SM = (NCH == 1) ? (BKV == 64 ? 3 : 2) : 1;
 };
 
-template <int NCH, int BKV, int KST>
+// ONES: row d of every head of V^T holds ones (d % 16 == 8), so column d of O = P V accumulates the
+// softmax row sums of the fp16-rounded P on the tensor core; the softmax warps then neither add up the
+// exponentials nor rescale a running sum (one FADD per score less on the latency-bound softmax path).
+template <int NCH, int BKV, int KST, bool ONES>
 __global__ void __launch_bounds__(ATT_THREADS, (NCH == 1) ? (BKV == 64 ? 3 : 2) : 1)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<NCH, BKV, KST>;
@@ -150,7 +154,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
 #pragma unroll
         for (int c = 0; c < BKV / 64; ++c)
           tma_load_3d(sV + stage * Cfg::V_STAGE + c * Cfg::V_CHUNK, &p.tmV, &kv_full[stage],
-                      kv0 + c * 64, head * p.d, kvimg);
+                      kv0 + c * 64, head * p.vt_head_rows, kvimg);
         if (++stage == KST) {
           stage = 0;
           phase ^= 1u;
@@ -267,7 +271,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       } else if (mx > m_used + ATT_RESCALE_THRESHOLD) {
         alpha = ex2_approx(m_used - mx);
         m_used = mx;
-        l_sum *= alpha;
+        if constexpr (!ONES) l_sum *= alpha;
         rescale = true;
       }
       // P_{j-1} V_{j-1} must have retired before P (single buffer) or O may be touched
@@ -301,7 +305,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
             const float x1 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used);
             // ATT_POLY_EXP: measured slower at the current MUFU utilisation (62 %): off by default
             const float p1 = (ATT_POLY_EXP && (e & 1)) ? ex2_poly3(x1) : ex2_approx(x1);
-            rsp[e & 1] += p0 + p1;
+            if constexpr (!ONES) rsp[e & 1] += p0 + p1;
             pk[e] = pack_half2(p0, p1);
           }
           const uint32_t col8 = c * 4 + q4;   // 8-column piece index inside the BKV tile
@@ -309,7 +313,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           st_shared_v4(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
       }
-      l_sum += rsp[0] + rsp[1];
+      if constexpr (!ONES) l_sum += rsp[0] + rsp[1];
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -318,7 +322,15 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     // ---- epilogue: O / l ----
     mbar_wait(pv_done, static_cast<uint32_t>((n_tiles - 1) & 1));
     tc_fence_after();
-    const float inv = 1.0f / l_sum;
+    float inv;
+    if constexpr (ONES) {
+      uint32_t o[16];
+      tmem_ld_x16(tO + static_cast<uint32_t>(p.d & ~15), o);   // d % 16 == 8: the sums sit in column 8
+      tmem_wait_ld();
+      inv = 1.0f / __uint_as_float(o[8]);
+    } else {
+      inv = 1.0f / l_sum;
+    }
     const int qrow = q0 + row;
     __half* dst = p.out + (static_cast<long long>(blockIdx.z) * p.lq + qrow) * p.ldo + head * p.d;
     for (int c = 0; c < p.dn; c += 16) {
@@ -349,13 +361,13 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   }
 }
 
-template <int NCH, int BKV, int KST>
+template <int NCH, int BKV, int KST, bool ONES>
 static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a,
                        cudaStream_t stream) {
   using Cfg = AttnCfg<NCH, BKV, KST>;
   static bool attr_set = false;
   if (!attr_set) {
-    MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<NCH, BKV, KST>,
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<NCH, BKV, KST, ONES>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
@@ -378,7 +390,7 @@ static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a
     if (encode_tmap_f16(&p.tmK, a->k, 4, dims, str, box)) return -1;
   }
   {
-    const uint64_t C = d * a->heads;
+    const uint64_t C = static_cast<uint64_t>(p.vt_head_rows) * a->heads;   // V^T rows per image
     uint64_t dims[3] = {static_cast<uint64_t>(a->lkv), C, static_cast<uint64_t>(a->nkv)};
     uint64_t str[3] = {0, static_cast<uint64_t>(a->ldvt) * 2, static_cast<uint64_t>(a->ldvt) * 2 * C};
     uint32_t box[3] = {64, static_cast<uint32_t>(p.dn), 1};
@@ -386,7 +398,7 @@ static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a
   }
   p.n_kv_tiles = (a->lkv + BKV - 1) / BKV;
   dim3 grid((a->lq + ATT_BQ - 1) / ATT_BQ, a->heads, a->nimg);
-  attn_tc_kernel<NCH, BKV, KST><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  attn_tc_kernel<NCH, BKV, KST, ONES><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   count_launch();
   MDK_CHECK_CUDA(cudaGetLastError());
   (void)ctx;
@@ -419,15 +431,21 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
   p.dn = p.dk16 * 16;
   p.kv_div = a->kv_div;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.vt_head_rows = a->vt_head_rows > 0 ? a->vt_head_rows : a->d;
+  MDK_REQUIRE(p.vt_head_rows >= a->d, "mdk_attn_fwd_f16: vt_head_rows < d");
+  if (a->vt_ones)
+    MDK_REQUIRE(a->d % 16 == 8 && p.vt_head_rows >= a->d + 8 && a->d <= 64,
+                "mdk_attn_fwd_f16: vt_ones needs d %% 16 == 8, d <= 64 and vt_head_rows >= d + 8");
   if (a->d <= 64) {
     static int bkv = -1;
     if (bkv < 0) {
       const char* e = getenv("MDK_ATTN_BKV");
       bkv = e ? atoi(e) : 128;   // measured: 128-key tiles x 2 CTAs/SM 1.97 ms vs 64 x 3 CTAs/SM 2.18 ms (L=9216, n=8)
     }
-    if (bkv == 128) return launch_attn<1, 128, 2>(ctx, p, a, stream);  // 2 CTAs per SM
-    return launch_attn<1, 64, 2>(ctx, p, a, stream);                     // 3 CTAs per SM
+    if (bkv == 64) return launch_attn<1, 64, 2, false>(ctx, p, a, stream);   // 3 CTAs per SM
+    if (a->vt_ones) return launch_attn<1, 128, 2, true>(ctx, p, a, stream);
+    return launch_attn<1, 128, 2, false>(ctx, p, a, stream);                  // 2 CTAs per SM
   }
-  if (a->d <= 128) return launch_attn<2, 128, 2>(ctx, p, a, stream);
-  return launch_attn<3, 64, 2>(ctx, p, a, stream);
+  if (a->d <= 128) return launch_attn<2, 128, 2, false>(ctx, p, a, stream);
+  return launch_attn<3, 64, 2, false>(ctx, p, a, stream);
 }

@@ -53,6 +53,7 @@ struct GemmParams {
   int out_trans[3];
   int trans_rows;
   long long trans_ld;
+  int trans_head_d, trans_head_dp;  // padded per-head rows of a transposed segment (0: dense)
   int dbg;  // MDK_GEMM_DEBUG bit 1 (perf triage only): skip the global stores of the epilogue
 };
 
@@ -521,10 +522,26 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             // per-image transposed store: lanes hold consecutive rows -> 64-byte runs per column
             const long long img = m / p.trans_rows;
             const long long l = m % p.trans_rows;
-            __half* dst = obase + (img * p.seg_cols + seg_col0 + c) * p.trans_ld + l;
+            if (p.trans_head_dp > 0) {
+              // channel (seg_col0 + c + j) = head * d + w  ->  row head * dp + w of this image
+              const int hd = p.trans_head_d, hdp = p.trans_head_dp;
+              int head = (seg_col0 + c) / hd, wch = (seg_col0 + c) % hd;
+              __half* ibase = obase + img * (p.seg_cols / hd) * hdp * p.trans_ld + l;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < nvalid) dst[static_cast<long long>(j) * p.trans_ld] = __float2half_rn(o[j]);
+              for (int j = 0; j < 32; ++j) {
+                if (j < nvalid)
+                  ibase[static_cast<long long>(head * hdp + wch) * p.trans_ld] = __float2half_rn(o[j]);
+                if (++wch == hd) {
+                  wch = 0;
+                  ++head;
+                }
+              }
+            } else {
+              __half* dst = obase + (img * p.seg_cols + seg_col0 + c) * p.trans_ld + l;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < nvalid) dst[static_cast<long long>(j) * p.trans_ld] = __float2half_rn(o[j]);
+              }
             }
           }
         }
@@ -635,6 +652,15 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
   p.seg_cols = a->seg_cols;
   p.trans_rows = a->trans_rows > 0 ? a->trans_rows : 1;
   p.trans_ld = a->trans_ld;
+  p.trans_head_d = 0;
+  p.trans_head_dp = 0;
+  if (a->trans_head_dp > 0) {
+    MDK_REQUIRE(a->trans_head_d > 0 && a->trans_head_dp >= a->trans_head_d && a->seg_cols > 0 &&
+                    a->seg_cols % a->trans_head_d == 0,
+                "mdk_gemm_f16: bad trans_head_d=%d trans_head_dp=%d", a->trans_head_d, a->trans_head_dp);
+    p.trans_head_d = a->trans_head_d;
+    p.trans_head_dp = a->trans_head_dp;
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {

@@ -253,21 +253,30 @@ class UNetEngine:
         h = ops.groupnorm(x, s.gnw, s.gnb, nimg=N, hw=hw, groups=self.groups, eps=1e-6, silu=False)
         h = ops.gemm(h, s.pin_w, bias=s.pin_b)
         lp = (hw + 7) // 8 * 8
+        # V^T per head padded to a multiple of 16 rows when d % 16 == 8 (d = 40): row d of every head is
+        # a row of ones, so the attention kernel's P.V MMA also yields the softmax row sums
+        ones = (d % 16 == 8) and d <= 64
+        dp = d + 8 if ones else d
+        th = (d, dp) if ones else None
         q = torch.empty((N * hw, C), dtype=F16, device=dev)
         k = torch.empty((N * hw, C), dtype=F16, device=dev)
-        vt = torch.empty((N, C, lp), dtype=F16, device=dev)
+        vt = torch.empty((N, self.heads * dp, lp), dtype=F16, device=dev)
+        if ones:
+            vt.view(N, self.heads, dp, lp)[:, :, d:].fill_(1.0)
         if bank is not None:
             r0 = n_uncond * hw
             n1, kvin = ops.layernorm(h, s.ln1w, s.ln1b, add=bank[r0:], add_row0=r0)
             if n_uncond > 0:     # CFG uncond half: plain self-attention (mutual_mix_attention.py:181-201)
                 ops.gemm(n1[:r0], s.wqkv, outs=[q[:r0], k[:r0], vt[:n_uncond]],
-                         trans=[False, False, True], trans_rows=hw)
+                         trans=[False, False, True], trans_rows=hw, trans_head=th)
             ops.gemm(n1[r0:], s.wq, out=q[r0:])
-            ops.gemm(kvin, s.wkv, outs=[k[r0:], vt[n_uncond:]], trans=[False, True], trans_rows=hw)
+            ops.gemm(kvin, s.wkv, outs=[k[r0:], vt[n_uncond:]], trans=[False, True], trans_rows=hw,
+                     trans_head=th)
         else:
             n1 = ops.layernorm(h, s.ln1w, s.ln1b)
-            ops.gemm(n1, s.wqkv, outs=[q, k, vt], trans=[False, False, True], trans_rows=hw)
-        a = ops.attention(q, k, vt, nimg=N, lq=hw, lkv=hw, heads=self.heads, d=d)
+            ops.gemm(n1, s.wqkv, outs=[q, k, vt], trans=[False, False, True], trans_rows=hw, trans_head=th)
+        a = ops.attention(q, k, vt, nimg=N, lq=hw, lkv=hw, heads=self.heads, d=d, vt_head_rows=dp,
+                          vt_ones=ones)
         h = ops.gemm(a, s.wo, bias=s.bo, residual=h)
         # CLIP cross-attention (mutual_mix_attention.py:206-220); K/V of the context once per call
         n2 = ops.layernorm(h, s.ln2w, s.ln2b)

@@ -83,7 +83,7 @@ def gemm(a0: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None
          row_div: int = 1, residual: Optional[torch.Tensor] = None, geglu: bool = False,
          conv: Optional[Tuple[int, int, int]] = None, out: Optional[torch.Tensor] = None,
          outs: Optional[Sequence[torch.Tensor]] = None, trans: Sequence[bool] = (False, False, False),
-         trans_rows: int = 0) -> torch.Tensor | Sequence[torch.Tensor]:
+         trans_rows: int = 0, trans_head: Optional[Tuple[int, int]] = None) -> torch.Tensor | Sequence[torch.Tensor]:
     """D = [a0 | a1] @ w^T with the fused epilogue of mdk_gemm_f16.
 
     a0/a1: [M, K_i] (conv=None) or NHWC [nimg, h, w, C_i] flattened to [M, C_i] with conv=(nimg,h,w)
@@ -141,7 +141,12 @@ def gemm(a0: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None
             args.out[s] = ptr(o)
             args.out_trans[s] = 1 if trans[s] else 0
             if trans[s]:
-                assert o.dim() == 3 and o.shape[1] == seg, o.shape
+                if trans_head is not None:
+                    hd, hdp = trans_head
+                    assert o.dim() == 3 and o.shape[1] == (seg // hd) * hdp, o.shape
+                    args.trans_head_d, args.trans_head_dp = hd, hdp
+                else:
+                    assert o.dim() == 3 and o.shape[1] == seg, o.shape
                 args.trans_ld = o.stride(1)
                 args.trans_rows = trans_rows
             else:
@@ -161,7 +166,7 @@ def gemm(a0: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, nimg: int, lq: int, lkv: int,
               heads: int, d: int, kv_div: int = 1, scale: Optional[float] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, vt_head_rows: int = 0, vt_ones: bool = False) -> torch.Tensor:
     """q [nimg*lq, heads*d], k [nkv*lkv, heads*d], vt [nkv, heads*d, ldvt] -> out [nimg*lq, heads*d]"""
     _chk16(q, "q"), _chk16(k, "k"), _chk16(vt, "vt")
     dev = q.device
@@ -173,6 +178,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, nimg: int, 
     a.nimg, a.nkv, a.kv_div = nimg, vt.shape[0], kv_div
     a.lq, a.lkv, a.heads, a.d = lq, lkv, heads, d
     a.scale = scale if scale is not None else 1.0 / math.sqrt(d)
+    a.vt_head_rows, a.vt_ones = vt_head_rows, 1 if vt_ones else 0
     _run(f"attn_tc:L={lq}x{lkv} d={d} n={nimg}" if _PROF is not None else "attn_tc",
          4.0 * nimg * heads * lq * lkv * d, 2.0 * heads * d * (2 * nimg * lq + 2 * vt.shape[0] * lkv),
          lambda: load_library().mdk_attn_fwd_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),

@@ -324,6 +324,22 @@ def check_attn():
         torch.cuda.synchronize()
         ok &= report(f"attn n={nimg} lq={lq} lkv={lkv} h={heads} d={d}", out,
                      ref_attention(q, k, vt, nimg, lq, lkv, heads, d, kv_div))
+    # padded V^T with a ones row per head: row sums come out of the P.V MMA
+    for (nimg, l, heads, d) in [(2, 1024, 8, 40), (3, 200, 8, 8), (1, 2304, 8, 40)]:
+        C_ = heads * d
+        dp = d + 8
+        q = rnd(nimg * l, C_).to(F16)
+        k = rnd(nimg * l, C_, seed=11).to(F16)
+        lp = (l + 7) // 8 * 8
+        v = rnd(nimg, heads, d, l, seed=12).to(F16)
+        vt = torch.full((nimg, heads, dp, lp), float("nan"), dtype=F16, device=DEV)
+        vt[:, :, :d, :l] = v
+        vt[:, :, d:, :] = 1.0
+        out = ops.attention(q, k, vt.reshape(nimg, heads * dp, lp), nimg=nimg, lq=l, lkv=l, heads=heads, d=d,
+                            vt_head_rows=dp, vt_ones=True)
+        vt_dense = torch.zeros(nimg, C_, lp, dtype=F16, device=DEV)
+        vt_dense[:, :, :l] = v.reshape(nimg, C_, l)
+        ok &= report(f"attn(ones) n={nimg} L={l} d={d}", out, ref_attention(q, k, vt_dense, nimg, l, l, heads, d, 1))
     return ok
 
 
@@ -466,6 +482,14 @@ def perf_attn():
         ms = timeit_ms(lambda: ops.attention(q, k, vt, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out))
         fl = 4.0 * nimg * heads * l * l * d
         print(f"perf attn n={nimg} L={l} d={d}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+        if d % 16 == 8:
+            dp = d + 8
+            vt2 = torch.ones(nimg, heads, dp, l, dtype=F16, device=DEV)
+            vt2[:, :, :d] = vt.reshape(nimg, heads, d, l)
+            vt2 = vt2.reshape(nimg, heads * dp, l)
+            ms = timeit_ms(lambda: ops.attention(q, k, vt2, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out,
+                                                 vt_head_rows=dp, vt_ones=True))
+            print(f"perf attn(ones) n={nimg} L={l} d={d}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
     return True
 
 
