@@ -354,7 +354,16 @@ def main():
                     kernels=kernels, top_shapes=shapes, cpu_baseline=cpu)
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # drop the captured graph (it holds NCCL work) before tearing the communicator down, and never
+        # let teardown hang the benchmark: the result line is already out
+        sys.stdout.flush()
+        loop.graph = None
+        torch.cuda.synchronize(dev)
+        try:
+            dist.barrier()
+        except Exception:  # noqa: BLE001
+            pass
+        os._exit(0)
 
 
 if __name__ == "__main__":
