@@ -117,7 +117,14 @@ def check_gemm_epilogue():
     ok &= report("seg q", q, ref3[:, :320])
     ok &= report("seg k", k, ref3[:, 320:640])
     ok &= report("seg vT", vt[:, :, :L].permute(0, 2, 1).reshape(M2, 320), ref3[:, 640:])
-    return ok
+    # the same with V^T padded per head (8 heads x 40 channels -> 48 rows each); pad rows untouched
+    vtp = torch.full((nimg, 8 * 48, Lp), 7.0, dtype=F16, device=DEV)
+    ops.gemm(a2, w3, outs=[q, k, vtp], trans=[False, False, True], trans_rows=L, trans_head=(40, 48))
+    got = vtp.reshape(nimg, 8, 48, Lp)[:, :, :40, :L].reshape(nimg, 320, L).permute(0, 2, 1).reshape(M2, 320)
+    ok &= report("seg vT padded heads", got, ref3[:, 640:])
+    pad_ok = bool((vtp.reshape(nimg, 8, 48, Lp)[:, :, 40:, :] == 7.0).all())
+    print(f"[{'OK ' if pad_ok else 'BAD'}] seg vT pad rows untouched", flush=True)
+    return ok and pad_ok
 
 
 def check_conv():
