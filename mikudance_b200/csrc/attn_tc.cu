@@ -71,14 +71,14 @@ struct AttnCfg {
   // head_dim <= 64: 3 CTAs/SM with 64-key tiles (64 KB smem, 128 TMEM columns, <= 112 registers) or
   // 2 CTAs/SM with 128-key tiles.  The softmax warps are latency-bound (ncu: MUFU 62 %, issue 45 % at
   // 2 CTAs/SM), so more independent CTAs per SM is what raises the MUFU utilisation.
-  static constexpr int CTAS_PER_SM = (NCH == 1) ? (BKV == 64 ? 3 : 2) : 1;
+  static constexpr int CTAS_PER_SM = (NCH == 1) ? (BKV == 64 ? 3 : 2) : ((NCH == 2 && BKV == 64) ? 2 : 1);
 };
 
 // ONES: row d of every head of V^T holds ones (d % 16 == 8), so column d of O = P V accumulates the
 // softmax row sums of the fp16-rounded P on the tensor core; the softmax warps then neither add up the
 // exponentials nor rescale a running sum (one FADD per score less on the latency-bound softmax path).
 template <int NCH, int BKV, int KST, bool ONES>
-__global__ void __launch_bounds__(ATT_THREADS, (NCH == 1) ? (BKV == 64 ? 3 : 2) : 1)
+__global__ void __launch_bounds__(ATT_THREADS, (NCH == 1) ? (BKV == 64 ? 3 : 2) : ((NCH == 2 && BKV == 64) ? 2 : 1))
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<NCH, BKV, KST>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -446,6 +446,14 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
     if (a->vt_ones) return launch_attn<1, 128, 2, true>(ctx, p, a, stream);
     return launch_attn<1, 128, 2, false>(ctx, p, a, stream);                  // 2 CTAs per SM
   }
-  if (a->d <= 128) return launch_attn<2, 128, 2, false>(ctx, p, a, stream);
+  if (a->d <= 128) {
+    static int bkv2 = -1;
+    if (bkv2 < 0) {
+      const char* e = getenv("MDK_ATTN_BKV2");
+      bkv2 = e ? atoi(e) : 128;
+    }
+    if (bkv2 == 64) return launch_attn<2, 64, 2, false>(ctx, p, a, stream);   // 2 CTAs per SM
+    return launch_attn<2, 128, 2, false>(ctx, p, a, stream);
+  }
   return launch_attn<3, 64, 2, false>(ctx, p, a, stream);
 }

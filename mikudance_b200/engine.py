@@ -83,6 +83,7 @@ class UNetEngine:
         import os
         # "a2a": two all-to-alls per motion module (default); "allgather": K/V all-gather per attention
         self.shard_mode = os.environ.get("MDK_SHARD_MODE", "a2a")
+        self.force_simt = False   # tests: run the gathered-layout temporal kernel on one GPU
         self.world = 1
         self.rank = 0
         self._pack()
@@ -297,33 +298,25 @@ class UNetEngine:
         image) and proj_out (per token) is per pixel, so once each rank holds ALL frames of hw/G
         pixels the temporal transformer needs no further communication.  Volume per module:
         2 * (G-1)/G of the local activation (4-16x less than the K/V all-gather)."""
-        import torch.distributed as dist
+        from .sharding import frames_to_pixels, pixels_per_rank, pixels_to_frames
         hw, C, G = H * W, o.c, self.world
-        pp = hw // G
+        pp = pixels_per_rank(hw, G)
         d = C // self.mheads
         g = ops.groupnorm(x, o.gnw, o.gnb, nimg=N, hw=hw, groups=self.groups, eps=1e-6, silu=False)
-        send = g.view(nb, fl, G, pp, C).permute(0, 2, 1, 3, 4).contiguous()      # [nb, G(dst), fl, pp, C]
-        recv = torch.empty_like(send)                                            # [nb, G(src), fl, pp, C]
-        for b in range(nb):
-            dist.all_to_all_single(recv[b], send[b], group=self.pg)
-        Mp = nb * f_total * pp                                                   # rows [(b f_total) pp]
-        h = ops.gemm(recv.view(Mp, C), o.pin_w, bias=o.pin_b)
+        h = frames_to_pixels(g, nb, fl, hw, G, self.pg)                          # rows [(b f_total) pp]
+        h = ops.gemm(h, o.pin_w, bias=o.pin_b)
         for e in o.att:
             n = ops.layernorm(h, e.lnw, e.lnb)
             qkv = ops.gemm(n, e.wqkv, row_bias=e.pe_qkv[:f_total], row_div=pp)
             a = ops.temporal_attention(qkv, nb=nb, f_q=f_total, npix=pp, heads=self.mheads, d=d)
             h = ops.gemm(a, e.wo, bias=e.bo, residual=h)
         h = self._ff(o, h, o.ffnw, o.ffnb)
-        back = torch.empty_like(send)                                            # [nb, G(pixel chunk), fl, pp, C]
-        hv = h.view(nb, G, fl, pp, C)
-        for b in range(nb):
-            dist.all_to_all_single(back[b], hv[b], group=self.pg)
-        hb = back.permute(0, 2, 1, 3, 4).contiguous().view(N * hw, C)
+        hb = pixels_to_frames(h, nb, fl, hw, G, self.pg)
         return ops.gemm(hb, o.pout_w, bias=o.pout_b, residual=x)
 
     def _motion(self, o, x, N, H, W, nb, fl, f_off, f_total):
         hw = H * W
-        if self.world > 1 and self.shard_mode == "a2a" and hw % self.world == 0:
+        if self.world > 1 and self.shard_mode == "a2a":
             return self._motion_a2a(o, x, N, H, W, nb, fl, f_total)
         C = o.c
         d = C // self.mheads
@@ -332,7 +325,7 @@ class UNetEngine:
         for e in o.att:
             n = ops.layernorm(h, e.lnw, e.lnb)
             pe_rows = e.pe_qkv[f_off:f_off + fl]        # frame j of this shard sits at window position f_off+j
-            if self.world == 1:
+            if self.world == 1 and not self.force_simt:
                 qkv = ops.gemm(n, e.wqkv, row_bias=pe_rows, row_div=hw)
                 a = ops.temporal_attention(qkv, nb=nb, f_q=fl, npix=hw, heads=self.mheads, d=d)
             else:
@@ -340,8 +333,11 @@ class UNetEngine:
                 qb = torch.empty((N * hw, C), dtype=F16, device=self.dev)
                 kv = torch.empty((N * hw, 2 * C), dtype=F16, device=self.dev)
                 ops.gemm(n, e.wqkv, outs=[qb, kv[:, :C], kv[:, C:]], row_bias=pe_rows, row_div=hw)
-                kv_all = torch.empty((self.world * N * hw, 2 * C), dtype=F16, device=self.dev)
-                dist.all_gather_into_tensor(kv_all, kv, group=self.pg)   # NCCL over NVLink
+                if self.world > 1:
+                    kv_all = torch.empty((self.world * N * hw, 2 * C), dtype=F16, device=self.dev)
+                    dist.all_gather_into_tensor(kv_all, kv, group=self.pg)   # NCCL over NVLink
+                else:
+                    kv_all = kv      # force_simt: the gathered-layout kernel on one GPU (multi-GPU parity anchor)
                 a = ops.temporal_attention(qb, nb=nb, f_q=fl, npix=hw, heads=self.mheads, d=d,
                                            kv=kv_all, f_kv=f_total, f_kv_rank=fl,
                                            f_q_offset=f_off, kv_offsets=(0, C))

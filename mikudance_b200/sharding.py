@@ -3,9 +3,12 @@
 Unit of work = one image = (CFG branch, frame) of a window.  Conv, GroupNorm (per frame), spatial /
 cross attention and feed-forwards never mix images; only the motion modules' temporal attention mixes
 the frames of one CFG branch at one pixel.  Rank r of G owns frames [r*fl, (r+1)*fl) of every window
-for both CFG branches; inside each motion module the K/V rows of all ranks are all-gathered (NCCL) and
-the temporal-attention kernel addresses frame j of batch b in the gathered buffer with
-`gathered_row()` below (the formula compiled into csrc/temporal_attn.cu).
+for both CFG branches.  Inside each motion module the activation is exchanged frame-sharded ->
+pixel-sharded (`frames_to_pixels`, one all-to-all), the whole temporal transformer runs on ALL frames
+of hw/G pixels with no further communication, and a second all-to-all (`pixels_to_frames`) brings it
+back.  The alternative mode all-gathers the temporal K/V rows of all ranks; the temporal-attention
+kernel then addresses frame j of batch b in the gathered buffer with `gathered_row()` below (the
+formula compiled into csrc/temporal_attn.cu).
 """
 from __future__ import annotations
 
@@ -36,3 +39,41 @@ def gathered_row(j: int, b: int, px: int, nb: int, fl: int, npix: int) -> int:
     """Row of frame j (window position), batch b, pixel px in the all-gathered [G, nb, fl, npix] K/V."""
     g, l = divmod(j, fl)
     return ((g * nb + b) * fl + l) * npix + px
+
+
+def pixels_per_rank(hw: int, world: int) -> int:
+    """Pixels each rank owns in the pixel-sharded layout (the last rank's tail is zero padding)."""
+    return (hw + world - 1) // world
+
+
+def frames_to_pixels(x: torch.Tensor, nb: int, fl: int, hw: int, world: int, group) -> torch.Tensor:
+    """x [(nb fl) hw, C], this rank's fl frames of every pixel  ->  [(nb F) pp, C] with F = world*fl:
+    ALL frames (window order: source rank major) of this rank's pp = ceil(hw / world) pixels.
+    Pixels >= hw (only when hw % world != 0) are zero rows."""
+    import torch.distributed as dist
+    C = x.shape[-1]
+    pp = pixels_per_rank(hw, world)
+    xv = x.view(nb, fl, hw, C)
+    if pp * world != hw:
+        pad = torch.zeros((nb, fl, pp * world - hw, C), dtype=x.dtype, device=x.device)
+        xv = torch.cat([xv, pad], dim=2)
+    send = xv.view(nb, fl, world, pp, C).permute(0, 2, 1, 3, 4).contiguous()   # [nb, G(dst), fl, pp, C]
+    recv = torch.empty_like(send)                                              # [nb, G(src), fl, pp, C]
+    for b in range(nb):
+        dist.all_to_all_single(recv[b], send[b], group=group)
+    return recv.view(nb * world * fl * pp, C)
+
+
+def pixels_to_frames(h: torch.Tensor, nb: int, fl: int, hw: int, world: int, group) -> torch.Tensor:
+    """Inverse of frames_to_pixels: h [(nb F) pp, C] -> [(nb fl) hw, C]."""
+    import torch.distributed as dist
+    C = h.shape[-1]
+    pp = pixels_per_rank(hw, world)
+    hv = h.view(nb, world, fl, pp, C)                                          # [nb, G(dst frames), fl, pp, C]
+    back = torch.empty_like(hv)                                                # [nb, G(pixel chunk), fl, pp, C]
+    for b in range(nb):
+        dist.all_to_all_single(back[b], hv[b], group=group)
+    out = back.permute(0, 2, 1, 3, 4).reshape(nb, fl, world * pp, C)
+    if pp * world != hw:
+        out = out[:, :, :hw]
+    return out.reshape(nb * fl * hw, C)

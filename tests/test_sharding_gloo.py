@@ -93,3 +93,53 @@ def test_uneven_window_is_rejected():
     with pytest.raises(ValueError):
         shard_window(list(range(30)), 0, 4)
     assert shard_window(list(range(32)), 3, 4) == (list(range(24, 32)), 24)
+
+
+def _worker_a2a(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mikudance_b200.sharding import frames_to_pixels, pixels_per_rank, pixels_to_frames
+        res = []
+        for hw in (6, 5, 1):                      # divisible, ragged, fewer pixels than ranks
+            nb, fl, C = 2, 3, 4
+            F_ = world * fl
+            # value encodes (b, frame, pixel, channel) so any misplaced row is visible
+            full = torch.arange(nb * F_ * hw * C, dtype=torch.float32).reshape(nb, F_, hw, C) + 1.0
+            mine = full[:, rank * fl:(rank + 1) * fl].reshape(nb * fl * hw, C).contiguous()
+            pp = pixels_per_rank(hw, world)
+            got = frames_to_pixels(mine, nb, fl, hw, world, None).reshape(nb, F_, pp, C)
+            want = torch.zeros(nb, F_, pp, C)
+            lo, hi = rank * pp, min((rank + 1) * pp, hw)
+            if hi > lo:
+                want[:, :, :hi - lo] = full[:, :, lo:hi]
+            ok_fwd = torch.equal(got, want)
+            back = pixels_to_frames(got.reshape(-1, C).contiguous(), nb, fl, hw, world, None)
+            ok_rt = torch.equal(back, mine)
+            res.append((hw, ok_fwd, ok_rt))
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_pixel_exchange_world2_gloo():
+    """frames_to_pixels / pixels_to_frames (the two all-to-alls of a frame-sharded motion module):
+    every rank ends up with ALL frames of its pixel slice in window order, and the round trip is the
+    identity — including pixel counts that do not divide by the GPU count."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_a2a, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in out) == [0, 1]
+    for _, res in out:
+        for hw, ok_fwd, ok_rt in res:
+            assert ok_fwd, f"frames_to_pixels misplaced rows (hw={hw})"
+            assert ok_rt, f"round trip is not the identity (hw={hw})"
