@@ -361,17 +361,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   }
 }
 
-template <int NCH, int BKV, int KST, bool ONES>
-static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a,
-                       cudaStream_t stream) {
-  using Cfg = AttnCfg<NCH, BKV, KST>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<NCH, BKV, KST, ONES>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+// Q / K: 4-D [d, heads, L, image] (box 64 x 1 x rows x 1); V^T: 3-D [L, heads * vt_head_rows, image]
+static int encode_attn_maps(AttnParams& p, const mdk_attn_args* a, int bkv) {
   const uint64_t d = static_cast<uint64_t>(a->d);
   {
     uint64_t dims[4] = {d, static_cast<uint64_t>(a->heads), static_cast<uint64_t>(a->lq),
@@ -386,7 +377,7 @@ static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a
                         static_cast<uint64_t>(a->nkv)};
     uint64_t str[4] = {0, d * 2, static_cast<uint64_t>(a->ldk) * 2,
                        static_cast<uint64_t>(a->ldk) * 2 * a->lkv};
-    uint32_t box[4] = {64, 1, BKV, 1};
+    uint32_t box[4] = {64, 1, static_cast<uint32_t>(bkv), 1};
     if (encode_tmap_f16(&p.tmK, a->k, 4, dims, str, box)) return -1;
   }
   {
@@ -396,9 +387,381 @@ static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a
     uint32_t box[3] = {64, static_cast<uint32_t>(p.dn), 1};
     if (encode_tmap_f16(&p.tmV, a->vt, 3, dims, str, box)) return -1;
   }
+  return 0;
+}
+
+template <int NCH, int BKV, int KST, bool ONES>
+static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a,
+                       cudaStream_t stream) {
+  using Cfg = AttnCfg<NCH, BKV, KST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<NCH, BKV, KST, ONES>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  if (encode_attn_maps(p, a, BKV)) return -1;
   p.n_kv_tiles = (a->lkv + BKV - 1) / BKV;
   dim3 grid((a->lq + ATT_BQ - 1) / ATT_BQ, a->heads, a->nimg);
   attn_tc_kernel<NCH, BKV, KST, ONES><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  count_launch();
+  MDK_CHECK_CUDA(cudaGetLastError());
+  (void)ctx;
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Ping-pong variant: one CTA = one (image, head, 256-query block) = two 128-row query tiles, each with
+// its own softmax warp group, S/O accumulators in TMEM and P buffer, sharing every K / V^T tile.
+// Why: with two independent 128-row CTAs per SM the softmax warps of both CTAs phase-lock (ncu source
+// counters: both sit on the MUFU.EX2 instructions at half rate, then both wait on the tensor core /
+// TMEM with the MUFU pipe idle: 62 % MUFU utilisation at d = 40 where the exponentials are the
+// bound).  Here a baton (two mbarriers) lets only ONE group at a time run its exp2 loop; the other
+// group meanwhile drains its next S tile, takes the row maxima, waits for its P V MMA and rescales —
+// so the MUFU pipe always has one warp per SM sub-partition feeding it.
+//   warp 0: TMA (Q block once, K / V^T ring of KST stages)   warp 1: MMA issuer
+//   warps 2-5: softmax group 0 (rows 0..127)                 warps 6-9: softmax group 1 (rows 128..255)
+// MMA order per K/V tile j: P_0 V_j, P_1 V_j, release stage j, then S_0 / S_1 of tile j+2 as soon as
+// the groups have drained tile j+1 (S is single-buffered per group, look-ahead of two tiles needs
+// KST >= 3).
+constexpr int ATT_PP_THREADS = 320;
+
+template <int NCH, int BKV, int KST>
+struct AttnPPCfg {
+  static constexpr int Q_TILE = NCH * ATT_BQ * 128;
+  static constexpr int K_STAGE = NCH * BKV * 128;
+  static constexpr int V_CHUNK = NCH * 64 * 128;
+  static constexpr int V_STAGE = (BKV / 64) * V_CHUNK;
+  static constexpr int P_TILE = (BKV / 64) * ATT_BQ * 128;
+  static constexpr int SMEM_BYTES = 2 * Q_TILE + KST * (K_STAGE + V_STAGE) + 2 * P_TILE + 256;
+  static constexpr uint32_t O_COL0 = 2 * BKV;        // S_g at column g * BKV, O_g at O_COL0 + g * 64 * NCH
+  static constexpr uint32_t TMEM_COLS = 512;
+  static_assert(2 * BKV + 2 * 64 * NCH <= 512, "TMEM budget");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+template <int NCH, int BKV, int KST, bool ONES>
+__global__ void __launch_bounds__(ATT_PP_THREADS, 1)
+attn_pp_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = AttnPPCfg<NCH, BKV, KST>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("mdk attn: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 2 * Cfg::Q_TILE;
+  uint8_t* sV = sK + KST * Cfg::K_STAGE;
+  uint8_t* sP = sV + KST * Cfg::V_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::P_TILE);
+  uint64_t* q_bar = bars;                     // [1]
+  uint64_t* kv_full = bars + 1;               // [KST]
+  uint64_t* kv_empty = bars + 1 + KST;        // [KST]
+  uint64_t* s_full = bars + 1 + 2 * KST;      // [2] S_g(j) complete in TMEM
+  uint64_t* s_free = s_full + 2;              // [2] S_g(j) drained into registers (4 warp arrivals)
+  uint64_t* p_full = s_full + 4;              // [2] P_g(j) in shared memory (4 warp arrivals)
+  uint64_t* pv_done = s_full + 6;             // [2] O_g += P_g(j) V_j retired
+  uint64_t* baton = s_full + 8;               // [2] group g may run its exp2 loop (4 warp arrivals)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * ATT_BQ);
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int kvimg = img / p.kv_div;
+  const int n_tiles = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_bar, 1);
+    for (int s = 0; s < KST; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_free[g], 4);
+      mbar_init(&p_full[g], 4);
+      mbar_init(&pv_done[g], 1);
+      mbar_init(&baton[g], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      mbar_expect_tx(q_bar, 2 * Cfg::Q_TILE);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          tma_load_4d(sQ + t * Cfg::Q_TILE + c * ATT_BQ * 128, &p.tmQ, q_bar, c * 64, head,
+                      q0 + t * ATT_BQ, img);
+      const uint32_t stage_bytes =
+          static_cast<uint32_t>(Cfg::K_STAGE + (BKV / 64) * p.dn * 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1u);
+        mbar_expect_tx(&kv_full[stage], stage_bytes);
+        const int kv0 = j * BKV;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          tma_load_4d(sK + stage * Cfg::K_STAGE + c * BKV * 128, &p.tmK, &kv_full[stage], c * 64,
+                      head, kv0, kvimg);
+#pragma unroll
+        for (int c = 0; c < BKV / 64; ++c)
+          tma_load_3d(sV + stage * Cfg::V_STAGE + c * Cfg::V_CHUNK, &p.tmV, &kv_full[stage],
+                      kv0 + c * 64, head * p.vt_head_rows, kvimg);
+        if (++stage == KST) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc_s = make_idesc_f16(ATT_BQ, BKV);
+    const uint32_t idesc_o = make_idesc_f16(ATT_BQ, static_cast<uint32_t>(p.dn));
+    auto issue_s = [&](int g, int stage) {
+      if (lane == 0) {
+        const uint32_t tS = tmem_base + static_cast<uint32_t>(g * BKV);
+        for (int ks = 0; ks < p.dk16; ++ks) {
+          const int c = ks >> 2, w = ks & 3;
+          const uint64_t adesc =
+              make_sdesc_sw128(smem_u32(sQ + g * Cfg::Q_TILE + c * ATT_BQ * 128)) + 2u * w;
+          const uint64_t bdesc =
+              make_sdesc_sw128(smem_u32(sK + stage * Cfg::K_STAGE + c * BKV * 128)) + 2u * w;
+          tc_mma_f16_ss(tS, adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(&s_full[g]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_bar, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    issue_s(1, 0);
+    if (n_tiles > 1) {
+      mbar_wait(&kv_full[1 % KST], 0);
+      for (int g = 0; g < 2; ++g) {
+        mbar_wait(&s_free[g], 0);
+        tc_fence_after();
+        issue_s(g, 1 % KST);
+      }
+    }
+    int stage = 0;                     // stage of tile j
+    int stage2 = 2 % KST;              // stage of tile j + 2
+    uint32_t phase2 = (2 / KST) & 1u;  // kv_full parity of tile j + 2
+    for (int j = 0; j < n_tiles; ++j) {
+      for (int g = 0; g < 2; ++g) {
+        mbar_wait(&p_full[g], static_cast<uint32_t>(j & 1));
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t tO = tmem_base + Cfg::O_COL0 + static_cast<uint32_t>(g * 64 * NCH);
+#pragma unroll
+          for (int ks = 0; ks < BKV / 16; ++ks) {
+            const int c = ks >> 2, w = ks & 3;
+            const uint64_t adesc =
+                make_sdesc_sw128(smem_u32(sP + g * Cfg::P_TILE + c * ATT_BQ * 128)) + 2u * w;
+            const uint64_t bdesc =
+                make_sdesc_sw128(smem_u32(sV + stage * Cfg::V_STAGE + c * Cfg::V_CHUNK)) + 2u * w;
+            tc_mma_f16_ss(tO, adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          }
+          tc_commit(&pv_done[g]);
+          if (g == 1) tc_commit(&kv_empty[stage]);   // both groups are through with K_j / V_j
+        }
+        __syncwarp();
+      }
+      if (j + 2 < n_tiles) {
+        mbar_wait(&kv_full[stage2], phase2);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&s_free[g], static_cast<uint32_t>((j + 1) & 1));
+          tc_fence_after();
+          issue_s(g, stage2);
+        }
+      }
+      if (++stage == KST) stage = 0;
+      if (++stage2 == KST) {
+        stage2 = 0;
+        phase2 ^= 1u;
+      }
+    }
+  } else {
+    // ======================= softmax groups =======================
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // query row inside the group's tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + static_cast<uint32_t>(g * BKV);
+    const uint32_t tO = tmem_base + lane_off + Cfg::O_COL0 + static_cast<uint32_t>(g * 64 * NCH);
+    float m_used = -INFINITY;
+    float l_sum = 0.f;
+    const uint32_t prow = smem_u32(sP + g * Cfg::P_TILE) + static_cast<uint32_t>(row) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    if (g == 1) {   // group 0 runs its first exp2 phase without waiting
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&baton[0]);
+    }
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[g], static_cast<uint32_t>(j & 1));
+      tc_fence_after();
+      uint32_t v[BKV / 32][32];
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) tmem_ld_x32(tS + c * 32, v[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);
+      const int nvalid = p.lkv - j * BKV;
+      if (nvalid < BKV) {
+#pragma unroll
+        for (int c = 0; c < BKV / 32; ++c) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (c * 32 + e >= nvalid) v[c][e] = 0xff800000u;  // -inf
+          }
+        }
+      }
+      float mx;
+      {
+        float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < BKV / 32; ++c) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mp[e & 3] = fmaxf(mp[e & 3], __uint_as_float(v[c][e]));
+        }
+        mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+      }
+      mx *= p.scale_log2;
+      float alpha = 1.0f;
+      bool rescale = false;
+      if (j == 0) {
+        m_used = mx;
+      } else if (mx > m_used + ATT_RESCALE_THRESHOLD) {
+        alpha = ex2_approx(m_used - mx);
+        m_used = mx;
+        if constexpr (!ONES) l_sum *= alpha;
+        rescale = true;
+      }
+      if (j > 0) {
+        mbar_wait(&pv_done[g], static_cast<uint32_t>((j - 1) & 1));
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, rescale)) {
+        for (int c = 0; c < p.dn; c += 16) {
+          uint32_t o[16];
+          tmem_ld_x16(tO + c, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+          tmem_st_x16(tO + c, o);
+        }
+        tmem_wait_st();
+      }
+      // ---- exclusive exp2 phase: only one group at a time feeds the MUFU pipe ----
+      mbar_wait(&baton[g], static_cast<uint32_t>(j & 1));
+      float rsp[2] = {0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 =
+                ex2_approx(fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e]), p.scale_log2, -m_used));
+            const float p1 =
+                ex2_approx(fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used));
+            if constexpr (!ONES) rsp[e & 1] += p0 + p1;
+            pk[e] = pack_half2(p0, p1);
+          }
+          const uint32_t col8 = c * 4 + q4;
+          const uint32_t cc = col8 >> 3, q = col8 & 7u;
+          st_shared_v4(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&baton[g ^ 1]);
+      if constexpr (!ONES) l_sum += rsp[0] + rsp[1];
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+    }
+    // ---- epilogue: O / l ----
+    mbar_wait(&pv_done[g], static_cast<uint32_t>((n_tiles - 1) & 1));
+    tc_fence_after();
+    float inv;
+    if constexpr (ONES) {
+      uint32_t o[16];
+      tmem_ld_x16(tO + static_cast<uint32_t>(p.d & ~15), o);
+      tmem_wait_ld();
+      inv = 1.0f / __uint_as_float(o[8]);
+    } else {
+      inv = 1.0f / l_sum;
+    }
+    const int qrow = q0 + g * ATT_BQ + row;
+    __half* dst = p.out + (static_cast<long long>(blockIdx.z) * p.lq + qrow) * p.ldo + head * p.d;
+    for (int c = 0; c < p.dn; c += 16) {
+      uint32_t o[16];
+      tmem_ld_x16(tO + c, o);
+      tmem_wait_ld();
+      if (qrow < p.lq) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (c + q * 8 < p.d) {
+            uint4 val;
+            val.x = pack_half2(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+            val.y = pack_half2(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+            val.z = pack_half2(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+            val.w = pack_half2(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c + q * 8) = val;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int NCH, int BKV, int KST, bool ONES>
+static int launch_attn_pp(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a,
+                          cudaStream_t stream) {
+  using Cfg = AttnPPCfg<NCH, BKV, KST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_pp_kernel<NCH, BKV, KST, ONES>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  if (encode_attn_maps(p, a, BKV)) return -1;
+  p.n_kv_tiles = (a->lkv + BKV - 1) / BKV;
+  dim3 grid((a->lq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), a->heads, a->nimg);
+  attn_pp_kernel<NCH, BKV, KST, ONES><<<grid, ATT_PP_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   count_launch();
   MDK_CHECK_CUDA(cudaGetLastError());
   (void)ctx;
@@ -436,6 +799,19 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
   if (a->vt_ones)
     MDK_REQUIRE(a->d % 16 == 8 && p.vt_head_rows >= a->d + 8 && a->d <= 64,
                 "mdk_attn_fwd_f16: vt_ones needs d %% 16 == 8, d <= 64 and vt_head_rows >= d + 8");
+  // ping-pong kernel (two query tiles per CTA) for the long self-attention sequences
+  static int pp = -1;
+  if (pp < 0) {
+    const char* e = getenv("MDK_ATTN_PP");
+    pp = e ? atoi(e) : 3;   // bit 0: head_dim <= 64, bit 1: head_dim <= 128
+  }
+  if (a->lq >= 2 * ATT_BQ && a->lkv >= 2 * ATT_BQ) {
+    if (a->d <= 64 && (pp & 1)) {
+      if (a->vt_ones) return launch_attn_pp<1, 128, 3, true>(ctx, p, a, stream);
+      return launch_attn_pp<1, 128, 3, false>(ctx, p, a, stream);
+    }
+    if (a->d > 64 && a->d <= 128 && (pp & 2)) return launch_attn_pp<2, 64, 3, false>(ctx, p, a, stream);
+  }
   if (a->d <= 64) {
     static int bkv = -1;
     if (bkv < 0) {

@@ -14,6 +14,13 @@
 // zero-filled by TMA, which is exactly the conv's zero padding.  The skip concat is a second
 // A source selected per channel block.
 //
+// CG = 2 (default for all but tiny problems): two CTAs of a cluster (one TPC) work as a pair on a
+// 256 x BN tile with tcgen05.mma.cta_group::2 — each CTA stages its own 128 rows of A and only HALF of
+// the B tile (BN/2 rows), the pair's tensor cores read both halves.  Per 128 x BN x 64 of MMA work an
+// SM then pulls 16 KB + BN*64 B from L2 instead of 16 KB + BN*128 B: the 128-row kernel is bound by
+// the ~64 B/clk L2->SM port, not by the tensor pipe (PERF.md).  The leader CTA (cluster rank 0) issues
+// all MMAs; its commits are multicast to both CTAs' barriers; both CTAs run their own epilogue.
+//
 // Algorithmic bytes per launch: 2*(M*K + N*K + M*N [+ M*N residual]) ; FLOPs 2*M*N*K.
 #include <stdlib.h>
 
@@ -41,6 +48,7 @@ struct GemmParams {
   int taps;
   int H, W, nimg, bw, bh, bn, tiles_w, tiles_h;
   int m_tiles, n_tiles;
+  int mp_tiles;   // ceil(m_tiles / CG): M tiles per CTA of a pair
   const float* bias;
   const float* row_bias;
   int row_div, row_mod;
@@ -57,20 +65,27 @@ struct GemmParams {
   int dbg;  // MDK_GEMM_DEBUG bit 1 (perf triage only): skip the global stores of the epilogue
 };
 
-template <int BN>
+template <int BN, int CG>
 struct GemmCfg {
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = BN / CG;                  // B rows this CTA stages
+  static constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN >= 192) ? 4 : (BN >= 160 ? 5 : 6);
   static constexpr int EPI_STAGING = EPI_WARPS * 2 * 32 * 64;  // per epilogue warp: output + residual sub-tile
+  static constexpr int EPI_BIAS = EPI_WARPS * 256;  // per epilogue warp: bias of the current chunk(s)
+  static constexpr int RING_BUDGET = 232448 - EPI_STAGING - EPI_BIAS - 256;
+  static constexpr int STAGES_CG1 = (BN >= 192) ? 4 : (BN >= 160 ? 5 : 6);
+  static constexpr int STAGES_FIT = RING_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = (CG == 1) ? STAGES_CG1 : (STAGES_FIT > 8 ? 8 : STAGES_FIT);
   static constexpr int TMEM_COLS = (2 * BN <= 32)    ? 32
                                    : (2 * BN <= 64)  ? 64
                                    : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256
                                                      : 512;
-  static constexpr int EPI_BIAS = EPI_WARPS * 256;  // per epilogue warp: bias of the current chunk(s)
   // dynamic shared memory is declared __align__(1024) (checked at run time): no alignment slack
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING + EPI_BIAS + 256 /*barriers*/;
+  static_assert(B_TILE_BYTES % 1024 == 0, "B stage tiles must keep the 1024-byte swizzle alignment");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(2 * STAGES + 4 <= 30, "barrier block");
 };
 
 // GELU with the exact (erf) formulation of diffusers' GEGLU.  erf by Abramowitz-Stegun 7.1.26
@@ -149,10 +164,10 @@ __device__ __forceinline__ void store_chunk_tma(const float (&o)[32], uint32_t b
   }
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;  // 1024-byte alignment required by the 128B swizzle atoms
@@ -173,6 +188,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pair: rank 0 is the leader (issues the MMAs, owns the full / tmem-empty barriers in use)
+  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_tile = (CG == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = (CG == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA0);
@@ -186,19 +205,25 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], EPI_WARPS * CG);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
   if (warp == 0) {
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+    if constexpr (CG == 2)
+      tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_ptr_smem);
+    else
+      tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2)
+    cluster_sync_all();   // the peer's barriers are initialised before anything may signal them
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.mp_tiles * p.n_tiles;   // tiles per CTA (pair tiles for CG == 2)
   const int kblocks_per_tap = p.kb0 + p.kb1;
   const int num_kb = p.taps * kblocks_per_tap;
 
@@ -207,10 +232,12 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      // pair mode: transaction bytes of both CTAs are counted on the leader's full barrier
+      const uint32_t full0_cluster = (CG == 2) ? mapa_shared(smem_u32(&full_bar[0]), 0) : 0u;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        const int n0 = n_tile * BN;
+        const int m_tile = (tile / p.n_tiles) * CG + cta_rank;   // may be a phantom tile past M (zero-filled)
+        const int n0 = n_tile * BN + cta_rank * Cfg::B_ROWS;      // pair mode: this CTA's half of the B tile
         int m0 = m_tile * BM;
         int img0 = 0, h0 = 0, w0 = 0;
         if (p.taps > 1) {
@@ -229,15 +256,26 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             const int kk = (src1 ? (kb - p.kb0) : kb) * BK;
             const int bcol = tap * p.ktap + (src1 ? p.k0 + kk : kk);
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             const CUtensorMap* ta = src1 ? &p.tmA1 : &p.tmA0;
-            if (p.taps > 1) {
-              tma_load_4d(smem_a + stage * A_TILE_BYTES, ta, &full_bar[stage], kk, w0 + dw, h0 + dh,
-                          img0);
+            if constexpr (CG == 2) {
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              const uint32_t fb = full0_cluster + static_cast<uint32_t>(stage) * 8u;
+              if (p.taps > 1) {
+                tma_load_4d_cg2(smem_a + stage * A_TILE_BYTES, ta, fb, kk, w0 + dw, h0 + dh, img0);
+              } else {
+                tma_load_2d_cg2(smem_a + stage * A_TILE_BYTES, ta, fb, kk, m0);
+              }
+              tma_load_2d_cg2(smem_b + stage * Cfg::B_TILE_BYTES, &p.tmB, fb, bcol, n0);
             } else {
-              tma_load_2d(smem_a + stage * A_TILE_BYTES, ta, &full_bar[stage], kk, m0);
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              if (p.taps > 1) {
+                tma_load_4d(smem_a + stage * A_TILE_BYTES, ta, &full_bar[stage], kk, w0 + dw, h0 + dh,
+                            img0);
+              } else {
+                tma_load_2d(smem_a + stage * A_TILE_BYTES, ta, &full_bar[stage], kk, m0);
+              }
+              tma_load_2d(smem_b + stage * Cfg::B_TILE_BYTES, &p.tmB, &full_bar[stage], bcol, n0);
             }
-            tma_load_2d(smem_b + stage * Cfg::B_TILE_BYTES, &p.tmB, &full_bar[stage], bcol, n0);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -247,13 +285,13 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    // ======================= MMA issuer (pair mode: leader CTA only) =======================
+    constexpr uint32_t idesc = make_idesc_f16(BM * CG, BN);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t acc_phase[2] = {0, 0};
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = (cta_rank == 0) ? first_tile : total_tiles; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       mbar_wait(&tempty_bar[acc], acc_phase[acc] ^ 1u);
       acc_phase[acc] ^= 1u;
@@ -268,11 +306,20 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
-            tc_mma_f16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k),
-                          bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if constexpr (CG == 2)
+              tc_mma_f16_ss_cg2(d_tmem, adesc + static_cast<uint64_t>(2 * k),
+                                bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              tc_mma_f16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k),
+                            bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);                       // frees the smem stage when MMAs retire
-          if (kb == num_kb - 1) tc_commit(&tfull_bar[acc]);   // accumulator complete
+          if constexpr (CG == 2) {
+            tc_commit_cg2(&empty_bar[stage], 3);                       // frees the stage in BOTH CTAs
+            if (kb == num_kb - 1) tc_commit_cg2(&tfull_bar[acc], 3);   // both epilogues may start
+          } else {
+            tc_commit(&empty_bar[stage]);                       // frees the smem stage when MMAs retire
+            if (kb == num_kb - 1) tc_commit(&tfull_bar[acc]);   // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -290,10 +337,12 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     const uint32_t bias_addr = smem_u32(smem_bias) + static_cast<uint32_t>(warp - 2) * 256u;
     uint32_t acc_phase[2] = {0, 0};
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    // pair mode: "accumulator drained" is reported to the leader's barrier (16 arrivals per tile)
+    const uint32_t tempty0_cluster = (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      const int m_tile = (tile / p.n_tiles) * CG + cta_rank;
       const int n0 = n_tile * BN;
       long long m;  // global output row of this thread, -1 if out of range
       if (p.taps > 1) {
@@ -548,16 +597,27 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2)
+          mbar_arrive_cluster(tempty0_cluster + static_cast<uint32_t>(acc) * 8u);
+        else
+          mbar_arrive(&tempty_bar[acc]);
+      }
     }
     if (p.tma_store && lane == 0) bulk_wait<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2)
+    cluster_sync_all();   // neither CTA exits (or frees TMEM) while its peer may still signal / read it
+  else
+    __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (CG == 2)
+      tmem_dealloc_cg2<Cfg::TMEM_COLS>(tmem_base);
+    else
+      tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -592,19 +652,56 @@ static int pow2_div(int x, int cap) {
   return r;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_gemm(const mdk_ctx* ctx, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;  // per kernel instantiation; benign race (idempotent)
+  static int max_clusters = 0;
   if (!attr_set) {
-    MDK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>,
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
+    if (CG == 2) {
+      // how many CTA pairs fit on the device at once (persistent kernel: launch no more than that)
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(static_cast<unsigned>(ctx->num_sms / 2 * 2));
+      qc.blockDim = dim3(GEMM_THREADS);
+      qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      int n = 0;
+      MDK_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, CG>, &qc));
+      MDK_REQUIRE(n > 0, "mdk_gemm_f16: no CTA pair of the 2-CTA GEMM fits on this device");
+      max_clusters = n < ctx->num_sms / 2 ? n : ctx->num_sms / 2;
+    }
     attr_set = true;
   }
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.mp_tiles * p.n_tiles;
+  if (CG == 2) {
+    const int clusters = total < max_clusters ? total : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    MDK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, p));
+    count_launch();
+    return 0;
+  }
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  gemm_tc_kernel<BN, CG><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   count_launch();
   MDK_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -698,13 +795,21 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
     MDK_REQUIRE(a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0,
                 "mdk_gemm_f16: residual must be 16-byte aligned with ldr %% 8 == 0");
 
+  // CTA pairs (256-row tiles, tcgen05.mma.cta_group::2) unless the problem has a single 128-row tile
+  // or MDK_GEMM_CG=1 asks for the single-CTA kernel
+  static int cg_env = -1;
+  if (cg_env < 0) {
+    const char* e = getenv("MDK_GEMM_CG");
+    cg_env = e ? atoi(e) : 2;
+  }
+  const int m_tiles_est = (a->m + BM - 1) / BM;   // (conv tiles are also 128 pixels)
+  const int cg = (cg_env == 2 && m_tiles_est >= 2) ? 2 : 1;
   int bn;
   if (a->geglu) {
     bn = 256;
     MDK_REQUIRE(a->n % 256 == 0, "mdk_gemm_f16: geglu needs n %% 256 == 0 (n=%d)", a->n);
   } else {
-    int m_tiles_est = (a->m + BM - 1) / BM;   // (conv tiles are also 128 pixels)
-    bn = pick_bn(a->n, a->seg_cols, nseg, m_tiles_est, ctx->num_sms);
+    bn = pick_bn(a->n, a->seg_cols, nseg, (m_tiles_est + cg - 1) / cg, ctx->num_sms / cg);
     MDK_REQUIRE(bn > 0, "mdk_gemm_f16: no tile width divides seg_cols=%d", a->seg_cols);
   }
   p.n_tiles = (a->n + bn - 1) / bn;
@@ -759,7 +864,7 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(a->n)};
     uint64_t str[2] = {0, static_cast<uint64_t>(a->ldb) * 2};
-    uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(bn / cg)};   // pair mode: each CTA loads half of the B tile
     if (encode_tmap_f16(&p.tmB, a->b, 2, dims, str, box)) return -1;
   }
 
@@ -799,13 +904,25 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
     }
   }
 
-  switch (bn) {
-    case 256: return launch_gemm<256>(ctx, p, stream);
-    case 192: return launch_gemm<192>(ctx, p, stream);
-    case 160: return launch_gemm<160>(ctx, p, stream);
-    case 128: return launch_gemm<128>(ctx, p, stream);
-    case 64: return launch_gemm<64>(ctx, p, stream);
-    case 32: return launch_gemm<32>(ctx, p, stream);
+  p.mp_tiles = (p.m_tiles + cg - 1) / cg;
+  if (cg == 2) {
+    switch (bn) {
+      case 256: return launch_gemm<256, 2>(ctx, p, stream);
+      case 192: return launch_gemm<192, 2>(ctx, p, stream);
+      case 160: return launch_gemm<160, 2>(ctx, p, stream);
+      case 128: return launch_gemm<128, 2>(ctx, p, stream);
+      case 64: return launch_gemm<64, 2>(ctx, p, stream);
+      case 32: return launch_gemm<32, 2>(ctx, p, stream);
+    }
+  } else {
+    switch (bn) {
+      case 256: return launch_gemm<256, 1>(ctx, p, stream);
+      case 192: return launch_gemm<192, 1>(ctx, p, stream);
+      case 160: return launch_gemm<160, 1>(ctx, p, stream);
+      case 128: return launch_gemm<128, 1>(ctx, p, stream);
+      case 64: return launch_gemm<64, 1>(ctx, p, stream);
+      case 32: return launch_gemm<32, 1>(ctx, p, stream);
+    }
   }
   return set_error("mdk_gemm_f16: internal: bad tile width %d", bn);
 }

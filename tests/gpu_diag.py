@@ -319,10 +319,18 @@ def check_attn():
     for (nimg, lq, lkv, heads, d, kv_div) in [(2, 128, 128, 8, 64, 1), (2, 256, 256, 8, 40, 1),
                                               (3, 144, 144, 8, 160, 1), (4, 576, 257, 8, 80, 2),
                                               (2, 1024, 1024, 8, 40, 1), (2, 64, 64, 8, 8, 1),
-                                              (2, 16, 16, 8, 32, 1), (1, 2304, 2304, 8, 80, 1)]:
+                                              (2, 16, 16, 8, 32, 1), (1, 2304, 2304, 8, 80, 1),
+                                              # two-query-tile (ping-pong) kernel: ragged lq / lkv, 2-3 kv tiles,
+                                              # d = 64 and d = 128 (chunk boundaries), large-score rescale path
+                                              (2, 300, 300, 8, 40, 1), (1, 520, 384, 4, 64, 1),
+                                              (2, 256, 640, 8, 128, 1), (1, 9216, 9216, 2, 40, 1),
+                                              (2, 1024, 1024, 8, 40, -6), (2, 768, 512, 8, 80, -6)]:
         C_ = heads * d
+        qscale = 1.0
+        if kv_div < 0:          # negative kv_div encodes a query gain: running max grows by > 2^8
+            qscale, kv_div = float(-kv_div), 1
         nkv = nimg // kv_div
-        q = rnd(nimg * lq, C_).to(F16)
+        q = (rnd(nimg * lq, C_) * qscale).to(F16)
         k = rnd(nkv * lkv, C_, seed=11).to(F16)
         lp = (lkv + 7) // 8 * 8
         vt = torch.zeros(nkv, C_, lp, dtype=F16, device=DEV)
