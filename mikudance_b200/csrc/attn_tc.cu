@@ -134,7 +134,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
 
   if (warp == 0) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    if (elect_one()) {   // single-thread region known to the compiler: no ELECT/R2UR loop per TMA
       mbar_expect_tx(q_bar, Cfg::Q_BYTES);
 #pragma unroll
       for (int c = 0; c < NCH; ++c)
@@ -168,7 +168,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     const uint32_t tS = tmem_base + Cfg::S_COL;
     const uint32_t tO = tmem_base + Cfg::O_COL;
     auto issue_s = [&](int stage) {
-      if (lane == 0) {
+      if (elect_one()) {
         for (int ks = 0; ks < p.dk16; ++ks) {
           const int c = ks >> 2, w = ks & 3;
           const uint64_t adesc = make_sdesc_sw128(smem_u32(sQ + c * ATT_BQ * 128)) + 2u * w;
@@ -202,7 +202,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       }
       mbar_wait(p_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
           const int c = ks >> 2, w = ks & 3;
@@ -503,7 +503,7 @@ attn_pp_kernel(const __grid_constant__ AttnParams p) {
 
   if (warp == 0) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    if (elect_one()) {   // single-thread region known to the compiler: no ELECT/R2UR loop per TMA
       mbar_expect_tx(q_bar, 2 * Cfg::Q_TILE);
 #pragma unroll
       for (int t = 0; t < 2; ++t)
@@ -538,7 +538,7 @@ attn_pp_kernel(const __grid_constant__ AttnParams p) {
     const uint32_t idesc_s = make_idesc_f16(ATT_BQ, BKV);
     const uint32_t idesc_o = make_idesc_f16(ATT_BQ, static_cast<uint32_t>(p.dn));
     auto issue_s = [&](int g, int stage) {
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t tS = tmem_base + static_cast<uint32_t>(g * BKV);
         for (int ks = 0; ks < p.dk16; ++ks) {
           const int c = ks >> 2, w = ks & 3;
@@ -572,7 +572,7 @@ attn_pp_kernel(const __grid_constant__ AttnParams p) {
       for (int g = 0; g < 2; ++g) {
         mbar_wait(&p_full[g], static_cast<uint32_t>(j & 1));
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t tO = tmem_base + Cfg::O_COL0 + static_cast<uint32_t>(g * 64 * NCH);
 #pragma unroll
           for (int ks = 0; ks < BKV / 16; ++ks) {

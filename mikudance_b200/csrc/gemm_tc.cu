@@ -140,10 +140,10 @@ __device__ __forceinline__ void store_chunk_coalesced(const float (&o)[32], uint
 // one elected lane issues an asynchronous bulk tensor store; bounds are clipped by TMA.  The wait for
 // the previous store sits at the top of the next chunk's store, i.e. behind that chunk's TMEM load,
 // bias / residual adds and conversion.
-__device__ __forceinline__ void store_chunk_tma(const float (&o)[32], uint32_t buf_addr, int lane,
+__device__ __forceinline__ void store_chunk_tma(const float (&o)[32], uint32_t buf_addr, int lane, bool leader,
                                                 const CUtensorMap* tm, bool conv, int c0, int c1, int c2,
                                                 int c3) {
-  if (lane == 0) bulk_wait_read<0>();  // the previous store has finished reading the staging buffer
+  if (leader) bulk_wait_read<0>();  // the previous store has finished reading the staging buffer
   __syncwarp();
   const uint32_t my = buf_addr + static_cast<uint32_t>(lane) * 64u;
   const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
@@ -155,7 +155,7 @@ __device__ __forceinline__ void store_chunk_tma(const float (&o)[32], uint32_t b
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (leader) {
     if (conv)
       tma_store_4d(tm, buf_addr, c0, c1, c2, c3);
     else
@@ -229,7 +229,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 
   if (warp == 0) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`): the compiler then knows a single thread runs this region and
+    // emits the uniform-datapath TMA / tcgen05 instructions directly instead of wrapping each one in
+    // an ELECT + R2UR.BROADCAST loop (measured: that loop, not the tensor pipe, paced the main loop)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       // pair mode: transaction bytes of both CTAs are counted on the leader's full barrier
@@ -300,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t adesc = make_sdesc_sw128(smem_u32(smem_a + stage * A_TILE_BYTES));
           const uint64_t bdesc = make_sdesc_sw128(smem_u32(smem_b + stage * Cfg::B_TILE_BYTES));
 #pragma unroll
@@ -337,6 +340,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     const uint32_t bias_addr = smem_u32(smem_bias) + static_cast<uint32_t>(warp - 2) * 256u;
     uint32_t acc_phase[2] = {0, 0};
     int it = 0;
+    const bool leader = elect_one();   // the lane that issues this warp's TMA stores / barrier arrivals
     // pair mode: "accumulator drained" is reported to the leader's barrier (16 arrivals per tile)
     const uint32_t tempty0_cluster = (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
@@ -390,24 +394,37 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
       const int m32 = static_cast<int>(m);  // M fits in int32 (checked on the host)
-      if (p.geglu) {
+      if (BN == 256 && p.geglu) {   // (the host only launches GEGLU with 256-wide tiles)
         // tile columns [0, BN/2) are values, [BN/2, BN) the matching gates
         constexpr int HALF = BN / 2;
+        constexpr int NCHUNK = (HALF + 63) / 64;   // 32-column chunks this warp handles per tile
         const int ocol0 = n_tile * HALF;
+        // the bias of this warp's value / gate columns is fetched BEFORE the wait for the accumulator
+        // (one column per lane); inside the chunk loop a global load would sit exposed between the
+        // TMEM load and its use (measured: the GEGLU epilogue, not the main loop, set the tile time)
+        float bpre_h[NCHUNK], bpre_g[NCHUNK];
+#pragma unroll
+        for (int i = 0; i < NCHUNK; ++i) {
+          const int cc = cgroup * 32 + i * 64;
+          const bool okc = p.bias != nullptr && cc < HALF && n0 + cc < p.N;
+          bpre_h[i] = okc ? __ldg(p.bias + n0 + cc + lane) : 0.f;
+          bpre_g[i] = okc ? __ldg(p.bias + n0 + HALF + cc + lane) : 0.f;
+        }
         mbar_wait(&tfull_bar[acc], acc_phase[acc]);
         acc_phase[acc] ^= 1u;
         tc_fence_after();
-        for (int c = cgroup * 32; c < HALF; c += 64) {
-          if (n0 + c >= p.N) break;
-          uint32_t vh[32], vg[32];
-          tmem_ld_x32(t_acc + c, vh);
-          tmem_ld_x32(t_acc + HALF + c, vg);
-          // bias of the 32 value and 32 gate columns: one global load per lane, read back as
-          // shared-memory broadcasts
+        uint32_t vh[32], vg[32];
+        if (cgroup * 32 < HALF && n0 + cgroup * 32 < p.N) {
+          tmem_ld_x32(t_acc + cgroup * 32, vh);
+          tmem_ld_x32(t_acc + HALF + cgroup * 32, vg);
+        }
+#pragma unroll
+        for (int i = 0; i < NCHUNK; ++i) {
+          const int c = cgroup * 32 + i * 64;
+          if (c >= HALF || n0 + c >= p.N) break;
           if (p.bias) {
-            sts32(bias_addr + static_cast<uint32_t>(lane) * 4u, __float_as_uint(__ldg(p.bias + n0 + c + lane)));
-            sts32(bias_addr + 128u + static_cast<uint32_t>(lane) * 4u,
-                  __float_as_uint(__ldg(p.bias + n0 + HALF + c + lane)));
+            sts32(bias_addr + static_cast<uint32_t>(lane) * 4u, __float_as_uint(bpre_h[i]));
+            sts32(bias_addr + 128u + static_cast<uint32_t>(lane) * 4u, __float_as_uint(bpre_g[i]));
           }
           __syncwarp();
           tmem_wait_ld();
@@ -427,6 +444,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             o[j4 * 4 + 2] = (__uint_as_float(vh[j4 * 4 + 2]) + bh.z) * gelu_erf(__uint_as_float(vg[j4 * 4 + 2]) + bg.z);
             o[j4 * 4 + 3] = (__uint_as_float(vh[j4 * 4 + 3]) + bh.w) * gelu_erf(__uint_as_float(vg[j4 * 4 + 3]) + bg.w);
           }
+          // the next chunk's accumulator load overlaps this chunk's residual add and store
+          if (i + 1 < NCHUNK && c + 64 < HALF && n0 + c + 64 < p.N) {
+            tmem_ld_x32(t_acc + c + 64, vh);
+            tmem_ld_x32(t_acc + HALF + c + 64, vg);
+          }
           __syncwarp();
           if (p.residual && m >= 0) {
             const __half* rsrc = p.residual + m * p.ldr + ocol0 + c;
@@ -444,7 +466,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           }
           if (!(p.dbg & 1)) {
             if (p.tma_store) {
-              store_chunk_tma(o, stage_addr, lane, &p.tmO[0], p.taps > 1, ocol0 + c, tc1, tc2, tc3);
+              store_chunk_tma(o, stage_addr, lane, leader, &p.tmO[0], p.taps > 1, ocol0 + c, tc1, tc2, tc3);
             } else {
               store_chunk_coalesced(o, stage_addr, lane, m32, p.out[0], p.ldo[0], ocol0 + c, 32);
             }
@@ -563,7 +585,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           if (p.dbg & 1) continue;
           if (!trans) {
             if (p.tma_store) {
-              store_chunk_tma(o, stage_addr, lane, &p.tmO[seg], p.taps > 1, seg_col0 + c, tc1, tc2, tc3);
+              store_chunk_tma(o, stage_addr, lane, leader, &p.tmO[seg], p.taps > 1, seg_col0 + c, tc1, tc2, tc3);
             } else {
               store_chunk_coalesced(o, stage_addr, lane, m32, obase, ldo, seg_col0 + c, nvalid);
             }
@@ -597,14 +619,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (leader) {
         if constexpr (CG == 2)
           mbar_arrive_cluster(tempty0_cluster + static_cast<uint32_t>(acc) * 8u);
         else
           mbar_arrive(&tempty_bar[acc]);
       }
     }
-    if (p.tma_store && lane == 0) bulk_wait<0>();
+    if (p.tma_store && leader) bulk_wait<0>();
   }
 
   tc_fence_before();
