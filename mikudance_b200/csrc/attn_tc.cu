@@ -203,8 +203,11 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       mbar_wait(p_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
       if (elect_one()) {
+        const int kv = p.lkv - j * BKV;                      // keys in this tile
+        const int ksteps = (kv >= BKV) ? (BKV / 16) : ((kv + 31) >> 5) * 2;   // whole 32-column chunks of P
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
+          if (ks >= ksteps) break;
           const int c = ks >> 2, w = ks & 3;
           const uint64_t adesc = make_sdesc_sw128(smem_u32(sP + c * ATT_BQ * 128)) + 2u * w;
           const uint64_t bdesc =
@@ -233,22 +236,26 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
+      // 32-column chunks of this tile that hold real keys (the last tile of a ragged sequence, e.g. the
+      // 257 CLIP tokens, may need only one): the others are neither loaded, exponentiated nor fed to P V
+      const int nvalid = p.lkv - j * BKV;  // columns >= nvalid are padding (last tile only)
+      const int nch = (nvalid >= BKV) ? (BKV / 32) : ((nvalid + 31) >> 5);
       uint32_t v[BKV / 32][32];
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) tmem_ld_x32(tS + c * 32, v[c]);
+      for (int c = 0; c < BKV / 32; ++c)
+        if (c < nch) tmem_ld_x32(tS + c * 32, v[c]);
       tmem_wait_ld();
       // S_j now lives in registers: the tensor core may overwrite it with S_{j+1}
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
-      const int nvalid = p.lkv - j * BKV;  // columns >= nvalid are padding (last tile only)
       float mx = -INFINITY;
       if (nvalid < BKV) {
 #pragma unroll
         for (int c = 0; c < BKV / 32; ++c) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            if (c * 32 + e >= nvalid) v[c][e] = 0xff800000u;  // -inf
+            if (c < nch && c * 32 + e >= nvalid) v[c][e] = 0xff800000u;  // -inf
           }
         }
       }
@@ -258,8 +265,10 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < BKV / 32; ++c) {
+          if (c < nch) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mp[e & 3] = fmaxf(mp[e & 3], __uint_as_float(v[c][e]));
+            for (int e = 0; e < 32; ++e) mp[e & 3] = fmaxf(mp[e & 3], __uint_as_float(v[c][e]));
+          }
         }
         mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
       }
@@ -295,6 +304,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       float rsp[2] = {0.f, 0.f};  // independent partial row sums (short dependency chains)
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) {
+        if (c >= nch) break;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           uint32_t pk[4];
@@ -574,8 +584,11 @@ attn_pp_kernel(const __grid_constant__ AttnParams p) {
         tc_fence_after();
         if (elect_one()) {
           const uint32_t tO = tmem_base + Cfg::O_COL0 + static_cast<uint32_t>(g * 64 * NCH);
+          const int kv = p.lkv - j * BKV;
+          const int ksteps = (kv >= BKV) ? (BKV / 16) : ((kv + 31) >> 5) * 2;
 #pragma unroll
           for (int ks = 0; ks < BKV / 16; ++ks) {
+            if (ks >= ksteps) break;
             const int c = ks >> 2, w = ks & 3;
             const uint64_t adesc =
                 make_sdesc_sw128(smem_u32(sP + g * Cfg::P_TILE + c * ATT_BQ * 128)) + 2u * w;
@@ -622,20 +635,24 @@ attn_pp_kernel(const __grid_constant__ AttnParams p) {
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[g], static_cast<uint32_t>(j & 1));
       tc_fence_after();
+      // 32-column chunks of this tile that hold real keys (the last tile of a ragged sequence, e.g. the
+      // 257 CLIP tokens, may need only one): the others are neither loaded, exponentiated nor fed to P V
+      const int nvalid = p.lkv - j * BKV;  // columns >= nvalid are padding (last tile only)
+      const int nch = (nvalid >= BKV) ? (BKV / 32) : ((nvalid + 31) >> 5);
       uint32_t v[BKV / 32][32];
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) tmem_ld_x32(tS + c * 32, v[c]);
+      for (int c = 0; c < BKV / 32; ++c)
+        if (c < nch) tmem_ld_x32(tS + c * 32, v[c]);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[g]);
-      const int nvalid = p.lkv - j * BKV;
       if (nvalid < BKV) {
 #pragma unroll
         for (int c = 0; c < BKV / 32; ++c) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            if (c * 32 + e >= nvalid) v[c][e] = 0xff800000u;  // -inf
+            if (c < nch && c * 32 + e >= nvalid) v[c][e] = 0xff800000u;  // -inf
           }
         }
       }
@@ -644,8 +661,10 @@ attn_pp_kernel(const __grid_constant__ AttnParams p) {
         float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < BKV / 32; ++c) {
+          if (c < nch) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mp[e & 3] = fmaxf(mp[e & 3], __uint_as_float(v[c][e]));
+            for (int e = 0; e < 32; ++e) mp[e & 3] = fmaxf(mp[e & 3], __uint_as_float(v[c][e]));
+          }
         }
         mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
       }
@@ -680,6 +699,7 @@ attn_pp_kernel(const __grid_constant__ AttnParams p) {
       float rsp[2] = {0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) {
+        if (c >= nch) break;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           uint32_t pk[4];
@@ -768,6 +788,355 @@ static int launch_attn_pp(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Split-key variant for head_dim <= 64 (the MUFU-bound L0 self-attention): the 128 keys of every S
+// tile are handled as two independent 64-key online-softmax streams by two softmax warp groups
+// (warps 2-5: keys 0..63, warps 6-9: keys 64..127 of each tile), each with its own running max, its
+// own lazy rescale, its own P half and its own accumulator O_h in TMEM (S 128 + O_0 64 + O_1 64 = 256
+// columns).  Nothing is exchanged per tile; the two partial results are merged once at the end:
+//     O = (2^(m0-m) O_0 + 2^(m1-m) O_1) / (2^(m0-m) l_0 + 2^(m1-m) l_1),  m = max(m0, m1).
+// Why: the exponentials bound this kernel (16 MUFU/clk/SM) and the softmax warps run them in a
+// dependent tmem-load -> max -> exp2 -> store chain; with 8 softmax warps per CTA and 2 CTAs per SM
+// there are 4 such chains per SM sub-partition instead of 2 to keep the MUFU pipe fed.
+// Needs lkv >= 128 (both streams see real keys in tile 0, so their running maxima are finite).
+constexpr int ATT_SK_THREADS = 320;
+constexpr int SK_BKV = 128;
+
+template <int KST, bool ONES>
+__global__ void __launch_bounds__(ATT_SK_THREADS, 2)
+attn_sk_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = AttnCfg<1, SK_BKV, KST>;
+  constexpr int BKV = SK_BKV;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("mdk attn: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + KST * Cfg::K_STAGE;
+  uint8_t* sP = sV + KST * Cfg::V_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_bar = bars;                    // [1]
+  uint64_t* kv_full = bars + 1;              // [KST]
+  uint64_t* kv_empty = bars + 1 + KST;       // [KST]
+  uint64_t* s_full = bars + 1 + 2 * KST;     // [1] S_j complete in TMEM
+  uint64_t* s_free = s_full + 1;             // [1] S_j drained into registers (8 warp arrivals)
+  uint64_t* p_full = s_full + 2;             // [2] P half h of tile j in shared memory (4 warp arrivals)
+  uint64_t* pv_done = s_full + 4;            // [2] O_h += P_h V_h retired
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int kvimg = img / p.kv_div;
+  const int n_tiles = p.n_kv_tiles;
+  constexpr uint32_t S_COL = 0, O_COL = BKV;   // O_h at O_COL + 64 h
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_bar, 1);
+    for (int s = 0; s < KST; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 8);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&p_full[h], 4);
+      mbar_init(&pv_done[h], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (elect_one()) {
+      mbar_expect_tx(q_bar, Cfg::Q_BYTES);
+      tma_load_4d(sQ, &p.tmQ, q_bar, 0, head, q0, img);
+      const uint32_t stage_bytes = static_cast<uint32_t>(Cfg::K_STAGE + (BKV / 64) * p.dn * 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1u);
+        mbar_expect_tx(&kv_full[stage], stage_bytes);
+        const int kv0 = j * BKV;
+        tma_load_4d(sK + stage * Cfg::K_STAGE, &p.tmK, &kv_full[stage], 0, head, kv0, kvimg);
+#pragma unroll
+        for (int c = 0; c < BKV / 64; ++c)
+          tma_load_3d(sV + stage * Cfg::V_STAGE + c * Cfg::V_CHUNK, &p.tmV, &kv_full[stage],
+                      kv0 + c * 64, head * p.vt_head_rows, kvimg);
+        if (++stage == KST) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc_s = make_idesc_f16(ATT_BQ, BKV);
+    const uint32_t idesc_o = make_idesc_f16(ATT_BQ, static_cast<uint32_t>(p.dn));
+    const uint32_t tS = tmem_base + S_COL;
+    auto issue_s = [&](int stage) {
+      if (elect_one()) {
+        for (int ks = 0; ks < p.dk16; ++ks) {
+          const uint64_t adesc = make_sdesc_sw128(smem_u32(sQ)) + 2u * ks;
+          const uint64_t bdesc = make_sdesc_sw128(smem_u32(sK + stage * Cfg::K_STAGE)) + 2u * ks;
+          tc_mma_f16_ss(tS, adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(s_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == KST) {
+        nstage = 0;
+        nphase ^= 1u;
+      }
+      if (j + 1 < n_tiles) {
+        mbar_wait(&kv_full[nstage], nphase);
+        mbar_wait(s_free, static_cast<uint32_t>(j & 1));
+        tc_fence_after();
+        issue_s(nstage);
+      }
+      const int kv = p.lkv - j * BKV;   // keys in this tile
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(&p_full[h], static_cast<uint32_t>(j & 1));
+        tc_fence_after();
+        if (elect_one()) {
+          const int kvh = kv - 64 * h;                                   // keys of this half
+          const int ksteps = (kvh >= 64) ? 4 : (kvh <= 0 ? 0 : ((kvh + 31) >> 5) * 2);
+          const uint32_t tO = tmem_base + O_COL + static_cast<uint32_t>(64 * h);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ks >= ksteps) break;
+            const uint64_t adesc = make_sdesc_sw128(smem_u32(sP + h * ATT_BQ * 128)) + 2u * ks;
+            const uint64_t bdesc =
+                make_sdesc_sw128(smem_u32(sV + stage * Cfg::V_STAGE + h * Cfg::V_CHUNK)) + 2u * ks;
+            tc_mma_f16_ss(tO, adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          }
+          tc_commit(&pv_done[h]);
+          if (h == 1) tc_commit(&kv_empty[stage]);
+        }
+        __syncwarp();
+      }
+      stage = nstage;
+      phase = nphase;
+    }
+  } else {
+    // ======================= softmax streams =======================
+    const int h = (warp - 2) >> 2;        // which 64-key half of every tile
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + S_COL + static_cast<uint32_t>(64 * h);
+    const uint32_t tO = tmem_base + lane_off + O_COL + static_cast<uint32_t>(64 * h);
+    float m_used = -INFINITY;
+    float l_sum = 0.f;
+    const uint32_t prow = smem_u32(sP) + static_cast<uint32_t>(h) * (ATT_BQ * 128) + static_cast<uint32_t>(row) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, static_cast<uint32_t>(j & 1));
+      tc_fence_after();
+      const int nvalid = p.lkv - j * BKV - 64 * h;   // keys of this half in this tile (may be <= 0)
+      const int nch = (nvalid >= 64) ? 2 : (nvalid <= 0 ? 0 : ((nvalid + 31) >> 5));
+      uint32_t v[2][32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        if (c < nch) tmem_ld_x32(tS + c * 32, v[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      if (nvalid < 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (c < nch && c * 32 + e >= nvalid) v[c][e] = 0xff800000u;  // -inf
+          }
+        }
+      }
+      float mx;
+      {
+        float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c < nch) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mp[e & 3] = fmaxf(mp[e & 3], __uint_as_float(v[c][e]));
+          }
+        }
+        mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+      }
+      mx *= p.scale_log2;
+      float alpha = 1.0f;
+      bool rescale = false;
+      if (nch > 0) {
+        if (j == 0) {
+          m_used = mx;
+        } else if (mx > m_used + ATT_RESCALE_THRESHOLD) {
+          alpha = ex2_approx(m_used - mx);
+          m_used = mx;
+          if constexpr (!ONES) l_sum *= alpha;
+          rescale = true;
+        }
+      }
+      // P_h(j-1) V_h(j-1) must have retired before P_h (single buffer) or O_h may be touched
+      if (j > 0) {
+        mbar_wait(&pv_done[h], static_cast<uint32_t>((j - 1) & 1));
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, rescale)) {
+        for (int c = 0; c < p.dn; c += 16) {
+          uint32_t o[16];
+          tmem_ld_x16(tO + c, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+          tmem_st_x16(tO + c, o);
+        }
+        tmem_wait_st();
+      }
+      float rsp[2] = {0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c >= nch) break;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 =
+                ex2_approx(fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e]), p.scale_log2, -m_used));
+            const float p1 =
+                ex2_approx(fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used));
+            if constexpr (!ONES) rsp[e & 1] += p0 + p1;
+            pk[e] = pack_half2(p0, p1);
+          }
+          const uint32_t q = static_cast<uint32_t>(c * 4 + q4);   // 16-byte piece inside the 64-key half
+          st_shared_v4(prow + ((q ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      if constexpr (!ONES) l_sum += rsp[0] + rsp[1];
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[h]);
+    }
+    // ---- merge the two streams: O / l ----
+    mbar_wait(&pv_done[h], static_cast<uint32_t>((n_tiles - 1) & 1));
+    tc_fence_after();
+    float l_mine;
+    if constexpr (ONES) {
+      uint32_t o[16];
+      tmem_ld_x16(tO + static_cast<uint32_t>(p.d & ~15), o);   // d % 16 == 8: the sums sit in column 8
+      tmem_wait_ld();
+      l_mine = __uint_as_float(o[8]);
+    } else {
+      l_mine = l_sum;
+    }
+    // every MMA has retired (both streams waited for their last P V): K / V / P shared memory is free
+    // and serves as the exchange buffer: stream 1 publishes (m, l, O_1 row), stream 0 merges and stores
+    named_bar_sync(1, 256);
+    float* xch = reinterpret_cast<float*>(sK) + static_cast<size_t>(row) * 68;   // 68 floats per row
+    if (h == 1) {
+      xch[0] = m_used;
+      xch[1] = l_mine;
+      for (int c = 0; c < p.dn; c += 16) {
+        uint32_t o[16];
+        tmem_ld_x16(tO + c, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) xch[4 + c + e] = __uint_as_float(o[e]);
+      }
+    }
+    named_bar_sync(1, 256);
+    if (h == 0) {
+      const float m1 = xch[0], l1 = xch[1];
+      const float m = fmaxf(m_used, m1);
+      const float a0 = ex2_approx(m_used - m), a1 = ex2_approx(m1 - m);
+      const float inv = 1.0f / (a0 * l_mine + a1 * l1);
+      const float w0 = a0 * inv, w1 = a1 * inv;
+      const int qrow = q0 + row;
+      __half* dst = p.out + (static_cast<long long>(blockIdx.z) * p.lq + qrow) * p.ldo + head * p.d;
+      for (int c = 0; c < p.dn; c += 16) {
+        uint32_t o[16];
+        tmem_ld_x16(tO + c, o);
+        tmem_wait_ld();
+        if (qrow < p.lq) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (c + q * 8 < p.d) {
+              float r[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                r[e] = __uint_as_float(o[q * 8 + e]) * w0 + xch[4 + c + q * 8 + e] * w1;
+              uint4 val;
+              val.x = pack_half2(r[0], r[1]);
+              val.y = pack_half2(r[2], r[3]);
+              val.z = pack_half2(r[4], r[5]);
+              val.w = pack_half2(r[6], r[7]);
+              *reinterpret_cast<uint4*>(dst + c + q * 8) = val;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+template <int KST, bool ONES>
+static int launch_attn_sk(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a,
+                          cudaStream_t stream) {
+  using Cfg = AttnCfg<1, SK_BKV, KST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_sk_kernel<KST, ONES>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  if (encode_attn_maps(p, a, SK_BKV)) return -1;
+  p.n_kv_tiles = (a->lkv + SK_BKV - 1) / SK_BKV;
+  dim3 grid((a->lq + ATT_BQ - 1) / ATT_BQ, a->heads, a->nimg);
+  attn_sk_kernel<KST, ONES><<<grid, ATT_SK_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  count_launch();
+  MDK_CHECK_CUDA(cudaGetLastError());
+  (void)ctx;
+  return 0;
+}
+
 }  // namespace mdk
 
 extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stream_) {
@@ -803,7 +1172,9 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
   static int pp = -1;
   if (pp < 0) {
     const char* e = getenv("MDK_ATTN_PP");
-    pp = e ? atoi(e) : 3;   // bit 0: head_dim <= 64, bit 1: head_dim <= 128
+    // bit 0: head_dim <= 64, bit 1: head_dim <= 128.  Measured (PERF.md): d = 80 0.818 vs 0.986 ms,
+    // d = 40 2.007 vs 1.897 ms -> only the wide heads use it by default
+    pp = e ? atoi(e) : 2;
   }
   if (a->lq >= 2 * ATT_BQ && a->lkv >= 2 * ATT_BQ) {
     if (a->d <= 64 && (pp & 1)) {
@@ -811,6 +1182,17 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
       return launch_attn_pp<1, 128, 3, false>(ctx, p, a, stream);
     }
     if (a->d > 64 && a->d <= 128 && (pp & 2)) return launch_attn_pp<2, 64, 3, false>(ctx, p, a, stream);
+  }
+  if (a->d <= 64 && a->lkv >= SK_BKV) {
+    static int sk = -1;
+    if (sk < 0) {
+      const char* e = getenv("MDK_ATTN_SK");
+      sk = e ? atoi(e) : 1;
+    }
+    if (sk) {
+      if (a->vt_ones) return launch_attn_sk<2, true>(ctx, p, a, stream);
+      return launch_attn_sk<2, false>(ctx, p, a, stream);
+    }
   }
   if (a->d <= 64) {
     static int bkv = -1;

@@ -817,15 +817,19 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
     MDK_REQUIRE(a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0,
                 "mdk_gemm_f16: residual must be 16-byte aligned with ldr %% 8 == 0");
 
-  // CTA pairs (256-row tiles, tcgen05.mma.cta_group::2) unless the problem has a single 128-row tile
-  // or MDK_GEMM_CG=1 asks for the single-CTA kernel
+  // CTA pairs (256-row tiles, tcgen05.mma.cta_group::2) for the main-loop-bound problems: measured
+  // (PERF.md) +18..21 % on the K >= 2880 convolutions, but -5..-20 % on the epilogue-bound K <= 640
+  // linears (both CTAs' epilogues gate the pair's next tile).  MDK_GEMM_CG=1 / =2 forces one kernel.
   static int cg_env = -1;
   if (cg_env < 0) {
     const char* e = getenv("MDK_GEMM_CG");
-    cg_env = e ? atoi(e) : 2;
+    cg_env = e ? atoi(e) : 0;
   }
   const int m_tiles_est = (a->m + BM - 1) / BM;   // (conv tiles are also 128 pixels)
-  const int cg = (cg_env == 2 && m_tiles_est >= 2) ? 2 : 1;
+  const long long num_kb_est = static_cast<long long>(a->conv_taps) * ((a->k0 + BK - 1) / BK + (a->k1 + BK - 1) / BK);
+  int cg = (num_kb_est >= 16) ? 2 : 1;
+  if (cg_env == 1 || cg_env == 2) cg = cg_env;
+  if (m_tiles_est < 2) cg = 1;
   int bn;
   if (a->geglu) {
     bn = 256;

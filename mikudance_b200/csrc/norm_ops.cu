@@ -3,6 +3,8 @@
 //
 // Algorithmic bytes: GroupNorm reads the input twice (stats pass + apply pass) and writes once:
 // 3 * 2 * nimg*hw*C bytes; LayerNorm reads once, writes once (twice with the bank output).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 #include "../../include/mdk.h"
@@ -307,6 +309,104 @@ __global__ void layernorm_kernel(const LnParams p) {
   }
 }
 
+// Rows of c = 40 * LPR halves (320 / 640 channels: LPR = 8 / 16): a group of LPR lanes owns a row and
+// every lane holds exactly 5 16-byte vectors, so all 32 lanes of every load carry data and each
+// group reads whole 128-byte lines (the generic kernel above runs 40- and 80-vector rows on 64 / 96
+// lane slots: 62 % / 83 % of the lanes busy).  RR rows per group in flight.
+template <int LPR, int RR>
+__global__ void layernorm_lpr_kernel(const LnParams p) {
+  constexpr int GPW = 32 / LPR;  // row groups per warp
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const long long w0 = static_cast<long long>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5);
+  const long long wstride = static_cast<long long>(gridDim.x) * warps_per_cta;
+  const float inv_c = 1.0f / static_cast<float>(p.c);
+  for (long long rb = w0 * (GPW * RR); rb < p.rows; rb += wstride * (GPW * RR)) {
+    uint4 raw[RR][5];
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+      const long long row = rb + r * GPW + grp;
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+        raw[r][i] = (row < p.rows) ? *reinterpret_cast<const uint4*>(p.x + row * p.c + (sub + i * LPR) * 8)
+                                   : make_uint4(0, 0, 0, 0);
+    }
+    float mean[RR], rstd[RR];
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const __half2* h = reinterpret_cast<const __half2*>(&raw[r][i]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          sum += f.x + f.y;
+        }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      mean[r] = sum * inv_c;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const __half2* h = reinterpret_cast<const __half2*>(&raw[r][i]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          const float d0 = f.x - mean[r], d1 = f.y - mean[r];
+          sq += d0 * d0 + d1 * d1;
+        }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      rstd[r] = rsqrtf(sq * inv_c + p.eps);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int cv = sub + i * LPR;
+      float gm[8], bt[8];
+      load8(p.gamma + cv * 8, gm);
+      load8(p.beta + cv * 8, bt);
+#pragma unroll
+      for (int r = 0; r < RR; ++r) {
+        const long long row = rb + r * GPW + grp;
+        if (row < p.rows) {
+          const __half2* h = reinterpret_cast<const __half2*>(&raw[r][i]);
+          float y[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            y[2 * e] = (f.x - mean[r]) * rstd[r] * gm[2 * e] + bt[2 * e];
+            y[2 * e + 1] = (f.y - mean[r]) * rstd[r] * gm[2 * e + 1] + bt[2 * e + 1];
+          }
+          store8(p.out + row * p.c + cv * 8, y);
+          if (p.add != nullptr && row >= p.add_row0) {
+            float ad[8];
+            const long long r2 = row - p.add_row0;
+            load8(p.add + r2 * p.c + cv * 8, ad);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] += ad[e];
+            store8(p.out2 + r2 * p.c + cv * 8, y);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int LPR, int RR>
+static void launch_ln_lpr(const LnParams& p, int num_sms, cudaStream_t stream) {
+  const int warps = 8;
+  const long long per_warp = (32 / LPR) * RR;
+  long long groups = (p.rows + per_warp - 1) / per_warp;
+  long long ctas = (groups + warps - 1) / warps;
+  const long long cap = static_cast<long long>(num_sms) * 8;
+  if (ctas > cap) ctas = cap;
+  layernorm_lpr_kernel<LPR, RR><<<static_cast<unsigned>(ctas), warps * 32, 0, stream>>>(p);
+}
+
 template <int NV, int R>
 static void launch_ln(const LnParams& p, int num_sms, cudaStream_t stream) {
   const int warps = 8;
@@ -356,24 +456,48 @@ extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* strea
   const int vx = ((V + 31) / 32) * 32;
   int vy = 512 / vx;
   if (vy < 1) vy = 1;
-  // enough CTAs to fill the machine a few times over, at least one pixel row of work each
-  int chunks = (ctx->num_sms * 8 + a->nimg - 1) / a->nimg;
-  const int max_chunks = (a->hw + vy - 1) / vy;
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
-  if (chunks < 1) chunks = 1;
-  p.pix_per_cta = (a->hw + chunks - 1) / chunks;
-  chunks = (a->hw + p.pix_per_cta - 1) / p.pix_per_cta;
-  p.nchunks = chunks;
   MDK_REQUIRE(a->groups <= vx * vy, "mdk_groupnorm_f16: too many groups");
-  dim3 block(vx, vy);
-  dim3 grid(chunks, a->nimg);
   const size_t stats_smem = (static_cast<size_t>(vx) * vy * 16 + 2 * static_cast<size_t>(C)) * sizeof(float);
   MDK_REQUIRE(stats_smem <= 48 * 1024, "mdk_groupnorm_f16: C=%d too large", C);
-  gn_stats_kernel<<<grid, block, stats_smem, stream>>>(p);
-  count_launch();
-  gn_apply_kernel<<<grid, block, 0, stream>>>(p);
-  count_launch();
+  // The apply pass re-reads what the statistics pass just read.  Running the two passes over groups of
+  // images small enough to stay in L2 (126 MB) turns that second read into L2 hits: HBM traffic
+  // 2 passes instead of 3.  MDK_GN_CHUNK_MB (default 48, 0 = whole batch in one go).
+  static int chunk_mb = -1;
+  if (chunk_mb < 0) {
+    const char* e = getenv("MDK_GN_CHUNK_MB");
+    chunk_mb = e ? atoi(e) : 48;
+  }
+  const long long img_bytes = static_cast<long long>(a->hw) * C * 2;
+  int img_per_group = a->nimg;
+  if (chunk_mb > 0) {
+    long long g = (static_cast<long long>(chunk_mb) << 20) / (img_bytes > 0 ? img_bytes : 1);
+    if (g < 1) g = 1;
+    if (g < img_per_group) img_per_group = static_cast<int>(g);
+  }
+  for (int i0 = 0; i0 < a->nimg; i0 += img_per_group) {
+    const int ni = (a->nimg - i0 < img_per_group) ? (a->nimg - i0) : img_per_group;
+    GnParams q = p;
+    q.nimg = ni;
+    q.x0 = p.x0 + static_cast<long long>(i0) * a->hw * a->c0;
+    if (p.x1) q.x1 = p.x1 + static_cast<long long>(i0) * a->hw * a->c1;
+    q.out = p.out + static_cast<long long>(i0) * a->hw * C;
+    q.ws = p.ws + static_cast<long long>(i0) * GN_MAX_CHUNKS * a->groups * 2;
+    // enough CTAs to fill the machine a few times over, at least one pixel row of work each
+    int chunks = (ctx->num_sms * 8 + ni - 1) / ni;
+    const int max_chunks = (a->hw + vy - 1) / vy;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
+    if (chunks < 1) chunks = 1;
+    q.pix_per_cta = (a->hw + chunks - 1) / chunks;
+    chunks = (a->hw + q.pix_per_cta - 1) / q.pix_per_cta;
+    q.nchunks = chunks;
+    dim3 block(vx, vy);
+    dim3 grid(chunks, ni);
+    gn_stats_kernel<<<grid, block, stats_smem, stream>>>(q);
+    count_launch();
+    gn_apply_kernel<<<grid, block, 0, stream>>>(q);
+    count_launch();
+  }
   MDK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -397,6 +521,20 @@ extern "C" int mdk_layernorm_f16(mdk_ctx* ctx, const mdk_ln_args* a, void* strea
   p.add = static_cast<const __half*>(a->add);
   p.out2 = static_cast<__half*>(a->out2);
   p.add_row0 = a->add_row0;
+  static int lpr_on = -1;
+  if (lpr_on < 0) {
+    const char* e = getenv("MDK_LN_LPR");
+    lpr_on = e ? atoi(e) : 1;
+  }
+  if (lpr_on && (a->c == 320 || a->c == 640)) {
+    if (a->c == 320)
+      launch_ln_lpr<8, 2>(p, ctx->num_sms, stream);
+    else
+      launch_ln_lpr<16, 2>(p, ctx->num_sms, stream);
+    count_launch();
+    MDK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   switch ((a->c / 8 + 31) / 32) {
     case 1: launch_ln<1, 4>(p, ctx->num_sms, stream); break;
     case 2: launch_ln<2, 3>(p, ctx->num_sms, stream); break;

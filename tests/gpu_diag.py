@@ -324,7 +324,9 @@ def check_attn():
                                               # d = 64 and d = 128 (chunk boundaries), large-score rescale path
                                               (2, 300, 300, 8, 40, 1), (1, 520, 384, 4, 64, 1),
                                               (2, 256, 640, 8, 128, 1), (1, 9216, 9216, 2, 40, 1),
-                                              (2, 1024, 1024, 8, 40, -6), (2, 768, 512, 8, 80, -6)]:
+                                              (2, 1024, 1024, 8, 40, -6), (2, 768, 512, 8, 80, -6),
+                                              # CLIP-length keys (257 = 2 tiles + 1 key), split-key kernel tails
+                                              (2, 512, 257, 8, 40, 1), (4, 200, 193, 4, 64, 2), (1, 384, 129, 8, 8, 1)]:
         C_ = heads * d
         qscale = 1.0
         if kv_div < 0:          # negative kv_div encodes a query gain: running max grows by > 2^8
@@ -505,6 +507,17 @@ def perf_attn():
             ms = timeit_ms(lambda: ops.attention(q, k, vt2, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out,
                                                  vt_head_rows=dp, vt_ones=True))
             print(f"perf attn(ones) n={nimg} L={l} d={d}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+    # cross-attention on the 257 CLIP tokens (2 CFG contexts shared by 16 frames each)
+    nimg, lq, lkv, heads, d = 32, 9216, 257, 8, 40
+    C_ = heads * d
+    q = rnd(nimg * lq, C_).to(F16)
+    k = rnd(2 * lkv, C_, seed=11).to(F16)
+    vt = torch.zeros(2, C_, 264, dtype=F16, device=DEV)
+    vt[:, :, :lkv] = rnd(2, C_, lkv, seed=12).to(F16)
+    out = torch.empty_like(q)
+    ms = timeit_ms(lambda: ops.attention(q, k, vt, nimg=nimg, lq=lq, lkv=lkv, heads=heads, d=d, kv_div=16, out=out))
+    fl = 4.0 * nimg * heads * lq * lkv * d
+    print(f"perf attn(cross) n={nimg} Lq={lq} Lkv={lkv} d={d}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
     return True
 
 
