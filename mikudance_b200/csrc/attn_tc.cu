@@ -1137,6 +1137,12 @@ static int launch_attn_sk(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args
   return 0;
 }
 
+// per-translation-unit copy of the try_wait time limit (see ptx.cuh); called by mdk_create
+int mdk_attn_set_wait_ns(unsigned ns) {
+  MDK_CHECK_CUDA(cudaMemcpyToSymbol(mdk_c_wait_ns, &ns, sizeof(ns)));
+  return 0;
+}
+
 }  // namespace mdk
 
 extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stream_) {
@@ -1169,9 +1175,9 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
     MDK_REQUIRE(a->d % 16 == 8 && p.vt_head_rows >= a->d + 8 && a->d <= 64,
                 "mdk_attn_fwd_f16: vt_ones needs d %% 16 == 8, d <= 64 and vt_head_rows >= d + 8");
   // ping-pong kernel (two query tiles per CTA) for the long self-attention sequences
-  static int pp = -1;
-  if (pp < 0) {
-    const char* e = getenv("MDK_ATTN_PP");
+  int pp;
+  {
+    const char* e = getenv("MDK_ATTN_PP");   // read per call: tests switch kernels in-process
     // bit 0: head_dim <= 64, bit 1: head_dim <= 128.  Measured (PERF.md): d = 80 0.818 vs 0.986 ms,
     // d = 40 2.007 vs 1.897 ms -> only the wide heads use it by default
     pp = e ? atoi(e) : 2;
@@ -1184,32 +1190,27 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
     if (a->d > 64 && a->d <= 128 && (pp & 2)) return launch_attn_pp<2, 64, 3, false>(ctx, p, a, stream);
   }
   if (a->d <= 64 && a->lkv >= SK_BKV) {
-    static int sk = -1;
-    if (sk < 0) {
-      const char* e = getenv("MDK_ATTN_SK");
-      sk = e ? atoi(e) : 1;
-    }
+    const char* e = getenv("MDK_ATTN_SK");
+    const int sk = e ? atoi(e) : 0;   // measured 2.068 vs 1.989 ms (L0 self-attention): off by default
     if (sk) {
       if (a->vt_ones) return launch_attn_sk<2, true>(ctx, p, a, stream);
       return launch_attn_sk<2, false>(ctx, p, a, stream);
     }
   }
   if (a->d <= 64) {
-    static int bkv = -1;
-    if (bkv < 0) {
-      const char* e = getenv("MDK_ATTN_BKV");
-      bkv = e ? atoi(e) : 128;   // measured: 128-key tiles x 2 CTAs/SM 1.97 ms vs 64 x 3 CTAs/SM 2.18 ms (L=9216, n=8)
-    }
+    // 128-key tiles x 2 CTAs/SM (1.99 ms at L = 9216, n = 8) vs 64-key tiles x 3 CTAs/SM (2.13 ms); the
+    // 64-key kernel wins when it pads the key sequence less (257 CLIP tokens: 320 vs 384 columns,
+    // 0.391 vs 0.474 ms)
+    const char* e = getenv("MDK_ATTN_BKV");
+    int bkv = e ? atoi(e) : 0;
+    if (bkv == 0) bkv = ((a->lkv + 63) / 64 * 64 < (a->lkv + 127) / 128 * 128) ? 64 : 128;
     if (bkv == 64) return launch_attn<1, 64, 2, false>(ctx, p, a, stream);   // 3 CTAs per SM
     if (a->vt_ones) return launch_attn<1, 128, 2, true>(ctx, p, a, stream);
     return launch_attn<1, 128, 2, false>(ctx, p, a, stream);                  // 2 CTAs per SM
   }
   if (a->d <= 128) {
-    static int bkv2 = -1;
-    if (bkv2 < 0) {
-      const char* e = getenv("MDK_ATTN_BKV2");
-      bkv2 = e ? atoi(e) : 128;
-    }
+    const char* e = getenv("MDK_ATTN_BKV2");
+    const int bkv2 = e ? atoi(e) : 128;
     if (bkv2 == 64) return launch_attn<2, 64, 2, false>(ctx, p, a, stream);   // 2 CTAs per SM
     return launch_attn<2, 128, 2, false>(ctx, p, a, stream);
   }

@@ -729,6 +729,12 @@ static int launch_gemm(const mdk_ctx* ctx, const GemmParams& p, cudaStream_t str
   return 0;
 }
 
+// per-translation-unit copy of the try_wait time limit (see ptx.cuh); called by mdk_create
+int mdk_gemm_set_wait_ns(unsigned ns) {
+  MDK_CHECK_CUDA(cudaMemcpyToSymbol(mdk_c_wait_ns, &ns, sizeof(ns)));
+  return 0;
+}
+
 }  // namespace mdk
 
 extern "C" int mdk_gemm_geglu_block(void) { return 256; }
@@ -820,9 +826,9 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
   // CTA pairs (256-row tiles, tcgen05.mma.cta_group::2) for the main-loop-bound problems: measured
   // (PERF.md) +18..21 % on the K >= 2880 convolutions, but -5..-20 % on the epilogue-bound K <= 640
   // linears (both CTAs' epilogues gate the pair's next tile).  MDK_GEMM_CG=1 / =2 forces one kernel.
-  static int cg_env = -1;
-  if (cg_env < 0) {
-    const char* e = getenv("MDK_GEMM_CG");
+  int cg_env;
+  {
+    const char* e = getenv("MDK_GEMM_CG");   // read per call: tests switch kernels in-process
     cg_env = e ? atoi(e) : 0;
   }
   const int m_tiles_est = (a->m + BM - 1) / BM;   // (conv tiles are also 128 pixels)

@@ -44,19 +44,42 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread until the phase completes or a time limit expires.  With the
+// system-dependent default limit a waiting warp came back every ~100-200 cycles: ncu counted 8 M
+// polls (x ~8 instructions of loop around each) in one L0 attention launch, 19 % of all issued
+// instructions, competing with the softmax warps for issue slots and for the MIO queue the MUFU
+// instructions also go through.  With an explicit limit (mdk_c_wait_ns > 0, set per device from
+// MDK_WAIT_NS by mdk_create; the compiler emits TRYWAIT + NANOSLEEP.SYNCS) a wait is a few
+// instructions.  One copy of the constant per translation unit (no relocatable device code).
+static __constant__ uint32_t mdk_c_wait_ns = 0;
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+  const uint32_t ns = mdk_c_wait_ns;
+  if (ns != 0u) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
   return ok != 0;
 }
+
 // Bounded wait: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
 // The watchdog uses the SM-local clock64 (cheap) and only starts after a burst of plain polls.
 #ifndef MDK_WAIT_LIMIT_CYCLES

@@ -57,6 +57,25 @@ def test_flash_attention_tcgen05():
     assert D.check_attn()
 
 
+@pytest.mark.parametrize("env", [{"MDK_ATTN_SK": "1"}, {"MDK_ATTN_PP": "3"}, {"MDK_ATTN_PP": "0"},
+                                 {"MDK_ATTN_BKV": "64"}, {"MDK_ATTN_BKV": "128", "MDK_ATTN_PP": "0"}])
+def test_flash_attention_alternative_kernels(monkeypatch, env):
+    """The kernels the dispatch heuristics do not pick by default (split-key, ping-pong for every
+    head size, 64-key tiles) stay parity-green: the switches are read per call."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    assert D.check_attn()
+
+
+@pytest.mark.parametrize("cg", ["1", "2"])
+def test_gemm_single_cta_and_cta_pair_kernels(monkeypatch, cg):
+    """Both GEMM kernels (128-row single CTA, 256-row cta_group::2 pair) on every shape / epilogue."""
+    monkeypatch.setenv("MDK_GEMM_CG", cg)
+    assert D.check_gemm_basic()
+    assert D.check_gemm_epilogue()
+    assert D.check_conv()
+
+
 def test_argument_errors_are_reported():
     from mikudance_b200 import _lib
     a = torch.randn(64, 36, device="cuda").half()          # K = 36 is not a multiple of 8
