@@ -15,6 +15,8 @@
 // Algorithmic FLOPs per launch: 4 * nimg * heads * lq * lkv * d.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "host_common.h"
 #include "ptx.cuh"
 #include "../../include/mdk.h"
@@ -24,21 +26,24 @@ namespace mdk {
 constexpr int ATT_BQ = 128;
 constexpr int ATT_THREADS = 192;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
-#ifndef MDK_ATT_POLY_EXP
-#define MDK_ATT_POLY_EXP 0
-#endif
-constexpr bool ATT_POLY_EXP = MDK_ATT_POLY_EXP != 0;
-
-// exp2 on the FMA/ALU pipes (Cody-Waite reduction + degree-3 minimax polynomial, max relative error
-// 7.5e-5 — below the fp16 rounding P gets anyway).  The d=40 self-attention is bound by the MUFU
-// pipe (one ex2 per score, 16/clk/SM), so a quarter of the exponentials is moved here.
-__device__ __forceinline__ float ex2_poly3(float x) {
-  x = fmaxf(x, -126.0f);
-  const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
-  const float n = t - 12582912.0f;
-  const float f = x - n;            // [-0.5, 0.5]
-  const float pl = fmaf(fmaf(fmaf(0.05517165f, f, 0.24261113f), f, 0.69326097f), f, 0.99992806f);
-  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+// exp2 of two scores at once on the FMA pipe, in half2 (P is rounded to fp16 anyway): round-to-nearest
+// split x = n + f through the magic constant 1551 = 0x660F (the low 5 bits of the sum are n + 15, the
+// fp16 exponent field of 2^n), degree-3 polynomial for 2^f on [-0.5, 0.5], product with 2^n.  13
+// issue slots per pair, none of them on the MUFU pipe / MIO queue that bound this kernel.
+__device__ __forceinline__ uint32_t ex2_poly_h2(float x0, float x1) {
+  const __half2 lo = __floats2half2_rn(-15.0f, -15.0f);
+  const __half2 magic = __floats2half2_rn(1551.0f, 1551.0f);
+  __half2 x = __hmax2(__floats2half2_rn(x0, x1), lo);
+  const __half2 t = __hadd2(x, magic);
+  const __half2 n = __hsub2(t, magic);
+  const __half2 f = __hsub2(x, n);
+  __half2 pl = __hfma2(__floats2half2_rn(0.05517165f, 0.05517165f), f, __floats2half2_rn(0.24261113f, 0.24261113f));
+  pl = __hfma2(pl, f, __floats2half2_rn(0.69326097f, 0.69326097f));
+  pl = __hfma2(pl, f, __floats2half2_rn(0.99992806f, 0.99992806f));
+  const uint32_t tb = *reinterpret_cast<const uint32_t*>(&t);
+  const uint32_t eb = (tb & 0x001F001Fu) << 10;
+  const __half2 r = __hmul2(pl, *reinterpret_cast<const __half2*>(&eb));
+  return *reinterpret_cast<const uint32_t*>(&r);
 }
 
 struct AttnParams {
@@ -52,6 +57,7 @@ struct AttnParams {
   int n_kv_tiles;
   float scale_log2;
   int vt_head_rows;  // rows per head in V^T (>= d)
+  int poly;          // 1: every second pair of exponentials on the FMA pipe (ex2_poly_h2)
 };
 
 template <int NCH, int BKV, int KST>
@@ -232,6 +238,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     float l_sum = 0.f;
     const uint32_t prow = smem_u32(sP) + static_cast<uint32_t>(row) * 128u;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
+    const bool poly = p.poly != 0;
 
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, static_cast<uint32_t>(j & 1));
@@ -302,27 +309,39 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       // exp2, row sum, fp16 pack and the store of P, 8 columns (one 16-byte piece) at a time.
       // P -> smem, K-major, 128B swizzle: 16-byte piece q of row r lands at piece (q ^ (r & 7))
       float rsp[2] = {0.f, 0.f};  // independent partial row sums (short dependency chains)
+      auto exp_tile = [&](auto poly_tag) {
+        constexpr bool POLY = decltype(poly_tag)::value;
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        if (c >= nch) break;
+        for (int c = 0; c < BKV / 32; ++c) {
+          if (c >= nch) break;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint32_t pk[4];
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float p0 =
-                ex2_approx(fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e]), p.scale_log2, -m_used));
-            const float x1 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used);
-            // ATT_POLY_EXP: measured slower at the current MUFU utilisation (62 %): off by default
-            const float p1 = (ATT_POLY_EXP && (e & 1)) ? ex2_poly3(x1) : ex2_approx(x1);
-            if constexpr (!ONES) rsp[e & 1] += p0 + p1;
-            pk[e] = pack_half2(p0, p1);
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e]), p.scale_log2, -m_used);
+              const float x1 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used);
+              if constexpr (POLY) {
+                if (e & 1) {
+                  pk[e] = ex2_poly_h2(x0, x1);   // FMA pipe, half2 (row sums come from the ones row of V^T)
+                  continue;
+                }
+              }
+              const float p0 = ex2_approx(x0);
+              const float p1 = ex2_approx(x1);
+              if constexpr (!ONES) rsp[e & 1] += p0 + p1;
+              pk[e] = pack_half2(p0, p1);
+            }
+            const uint32_t col8 = c * 4 + q4;   // 8-column piece index inside the BKV tile
+            const uint32_t cc = col8 >> 3, q = col8 & 7u;
+            st_shared_v4(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
-          const uint32_t col8 = c * 4 + q4;   // 8-column piece index inside the BKV tile
-          const uint32_t cc = col8 >> 3, q = col8 & 7u;
-          st_shared_v4(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
-      }
+      };
+      if (ONES && poly)
+        exp_tile(std::true_type{});
+      else
+        exp_tile(std::false_type{});
       if constexpr (!ONES) l_sum += rsp[0] + rsp[1];
       fence_proxy_async_smem();
       tc_fence_before();
@@ -1170,6 +1189,10 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
   p.kv_div = a->kv_div;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.vt_head_rows = a->vt_head_rows > 0 ? a->vt_head_rows : a->d;
+  {
+    const char* e = getenv("MDK_ATTN_POLY");
+    p.poly = e ? atoi(e) : 0;
+  }
   MDK_REQUIRE(p.vt_head_rows >= a->d, "mdk_attn_fwd_f16: vt_head_rows < d");
   if (a->vt_ones)
     MDK_REQUIRE(a->d % 16 == 8 && p.vt_head_rows >= a->d + 8 && a->d <= 64,

@@ -453,7 +453,16 @@ extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* strea
   p.out = static_cast<__half*>(a->out);
   p.ws = static_cast<float*>(a->ws);
   const int V = C / 8;
-  const int vx = ((V + 31) / 32) * 32;
+  // blockDim.x = V exactly (not rounded up to a warp multiple): thread (x, y) reads vector x of pixel
+  // y, so with a single source the linear thread id walks memory contiguously and every lane of
+  // every warp carries data (C = 320: 40 vectors per pixel; a 64-wide block left 37 % of the lanes
+  // idle).  MDK_GN_VX32=1 restores the rounded width.
+  static int vx32 = -1;
+  if (vx32 < 0) {
+    const char* e = getenv("MDK_GN_VX32");
+    vx32 = e ? atoi(e) : 0;
+  }
+  const int vx = vx32 ? ((V + 31) / 32) * 32 : V;
   int vy = 512 / vx;
   if (vy < 1) vy = 1;
   MDK_REQUIRE(a->groups <= vx * vy, "mdk_groupnorm_f16: too many groups");

@@ -58,7 +58,8 @@ def test_flash_attention_tcgen05():
 
 
 @pytest.mark.parametrize("env", [{"MDK_ATTN_SK": "1"}, {"MDK_ATTN_PP": "3"}, {"MDK_ATTN_PP": "0"},
-                                 {"MDK_ATTN_BKV": "64"}, {"MDK_ATTN_BKV": "128", "MDK_ATTN_PP": "0"}])
+                                 {"MDK_ATTN_BKV": "64"}, {"MDK_ATTN_BKV": "128", "MDK_ATTN_PP": "0"},
+                                 {"MDK_ATTN_POLY": "1"}])
 def test_flash_attention_alternative_kernels(monkeypatch, env):
     """The kernels the dispatch heuristics do not pick by default (split-key, ping-pong for every
     head size, 64-key tiles) stay parity-green: the switches are read per call."""
