@@ -189,6 +189,19 @@ def cpu_reference_sample(h, steps_cfg, reps, warm, budget_s=150.0):
     return t, fps, cores, note
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (average over the launches of one step) from
+    the committed ncu launch list of `bench.py --ncu-step` (profiles/r01_ncu_step_traffic.json, written by
+    scripts/ncu_summarise.py); None when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_step_traffic.json")) as f:
+            d = json.load(f)[kernel]
+        return dict(bytes_per_launch=d["dram_bytes"] / d["launches"], launches=d["launches"],
+                    dram_bytes_per_step=d["dram_bytes"], source=d.get("source", "ncu"))
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -199,7 +212,12 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-profile", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="run ONE eager step inside a cudaProfilerStart/Stop range and exit "
+                         "(for `ncu --profile-from-start off`; prints no bench line)")
     args = ap.parse_args()
+    if args.ncu_step:
+        args.no_graph = True
     h, F_, num_steps, ctx_frames = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -274,6 +292,15 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    if args.ncu_step:
+        loop.step(0)                      # warm (tensor maps, allocator)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        loop.step(1)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        print(json.dumps(dict(ncu_step=True, launches_per_step=launches_per_step)))
+        return
     # ---- device-resident timing ----
     for i in range(args.warmup):
         loop.step(i % num_steps)
@@ -318,7 +345,7 @@ def main():
             ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
             roofline = dict(kernel="gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv, all launches of one step)",
                             bound="tensor", achieved=ach, peak=peaks["tflops_sustained"], unit="TFLOP/s",
-                            frac=ach / peaks["tflops_sustained"], traffic=None,
+                            frac=ach / peaks["tflops_sustained"], traffic=ncu_traffic("gemm_tc_kernel"),
                             launches=g["n"], share_of_step=g["ms"] / sum(k["ms"] for k in kernels.values()),
                             peak_source=peaks["source"] + ", sustained bf16 GEMM")
     step_tflop = frame_evals * 2 * sum(per_image_flops(h, min(F_, ctx_frames)).values()) / 1e12 \

@@ -103,15 +103,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   uint64_t* kv_empty = bars + 1 + KST;       // [KST]
   uint64_t* s_full = bars + 1 + 2 * KST;     // [1] S_j complete in TMEM
   uint64_t* s_free = bars + 2 + 2 * KST;     // [1] S_j drained into registers (4 warp arrivals)
-  // P is handed over per 64-key chunk (NPC chunks per tile): while the tensor core consumes chunk c
-  // of tile j the softmax warps already write chunk c+1 (and chunk c of tile j+1 once its MMA has
-  // retired, which it long has): the P V MMA is off the softmax critical path without a second P
-  // buffer.  Measured before this split: replacing half of the MUFU exponentials by FMA-pipe
-  // polynomials changed nothing, i.e. the loop was bound by the exp -> P V -> exp hand-off latency.
-  uint64_t* p_full = bars + 3 + 2 * KST;     // [NPC <= 2] chunk c of P_j in shared memory (4 warp arrivals)
-  uint64_t* pv_done = bars + 5 + 2 * KST;    // [NPC <= 2] O += P_j[:, chunk c] V_j[chunk c] retired
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 7 + 2 * KST);
-  constexpr int NPC = BKV / 64;
+  uint64_t* p_full = bars + 3 + 2 * KST;     // [1]
+  uint64_t* pv_done = bars + 4 + 2 * KST;    // [1]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5 + 2 * KST);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -134,10 +128,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     }
     mbar_init(s_full, 1);
     mbar_init(s_free, 4);
-    for (int c = 0; c < 2; ++c) {
-      mbar_init(&p_full[c], 4);  // one arrive per softmax warp
-      mbar_init(&pv_done[c], 1);
-    }
+    mbar_init(p_full, 4);  // one arrive per softmax warp
+    mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
@@ -214,26 +206,22 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         tc_fence_after();
         issue_s(nstage);
       }
-      const int kv = p.lkv - j * BKV;                      // keys in this tile
-      const int ksteps = (kv >= BKV) ? (BKV / 16) : ((kv + 31) >> 5) * 2;   // whole 32-column chunks of P
+      mbar_wait(p_full, static_cast<uint32_t>(j & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const int kv = p.lkv - j * BKV;                      // keys in this tile
+        const int ksteps = (kv >= BKV) ? (BKV / 16) : ((kv + 31) >> 5) * 2;   // whole 32-column chunks of P
 #pragma unroll
-      for (int c = 0; c < NPC; ++c) {
-        mbar_wait(&p_full[c], static_cast<uint32_t>(j & 1));
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const int ks = c * 4 + w;
-            if (ks >= ksteps) break;
-            const uint64_t adesc = make_sdesc_sw128(smem_u32(sP + c * ATT_BQ * 128)) + 2u * w;
-            const uint64_t bdesc =
-                make_sdesc_sw128(smem_u32(sV + stage * Cfg::V_STAGE + c * Cfg::V_CHUNK)) + 2u * w;
-            tc_mma_f16_ss(tO, adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-          }
-          if (c == NPC - 1) tc_commit(&kv_empty[stage]);
-          tc_commit(&pv_done[c]);
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          if (ks >= ksteps) break;
+          const int c = ks >> 2, w = ks & 3;
+          const uint64_t adesc = make_sdesc_sw128(smem_u32(sP + c * ATT_BQ * 128)) + 2u * w;
+          const uint64_t bdesc =
+              make_sdesc_sw128(smem_u32(sV + stage * Cfg::V_STAGE + c * Cfg::V_CHUNK)) + 2u * w;
+          tc_mma_f16_ss(tO, adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         }
-        __syncwarp();
+        tc_commit(&kv_empty[stage]);
+        tc_commit(pv_done);
       }
       __syncwarp();
       stage = nstage;
@@ -302,12 +290,12 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         if constexpr (!ONES) l_sum *= alpha;
         rescale = true;
       }
+      // P_{j-1} V_{j-1} must have retired before P (single buffer) or O may be touched
+      if (j > 0) {
+        mbar_wait(pv_done, static_cast<uint32_t>((j - 1) & 1));
+        tc_fence_after();
+      }
       if (__any_sync(0xffffffffu, rescale)) {
-        // (rare) every P V MMA of tile j-1 must have retired before O is touched
-        if (j > 0) {
-          mbar_wait(&pv_done[NPC - 1], static_cast<uint32_t>((j - 1) & 1));
-          tc_fence_after();
-        }
         for (int c = 0; c < p.dn; c += 16) {
           uint32_t o[16];
           tmem_ld_x16(tO + c, o);
@@ -324,43 +312,30 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       auto exp_tile = [&](auto poly_tag) {
         constexpr bool POLY = decltype(poly_tag)::value;
 #pragma unroll
-        for (int cc = 0; cc < NPC; ++cc) {
-          // chunk cc of P_{j-1} must have been consumed before it is overwritten
-          if (j > 0) {
-            mbar_wait(&pv_done[cc], static_cast<uint32_t>((j - 1) & 1));
-            tc_fence_after();
-          }
+        for (int c = 0; c < BKV / 32; ++c) {
+          if (c >= nch) break;
 #pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2) {
-            const int c = cc * 2 + c2;
-            if (c < nch) {
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t pk[4];
 #pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float x0 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e]), p.scale_log2, -m_used);
-                  const float x1 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used);
-                  if constexpr (POLY) {
-                    if (e & 1) {
-                      pk[e] = ex2_poly_h2(x0, x1);   // FMA pipe, half2 (row sums: ones row of V^T)
-                      continue;
-                    }
-                  }
-                  const float p0 = ex2_approx(x0);
-                  const float p1 = ex2_approx(x1);
-                  if constexpr (!ONES) rsp[e & 1] += p0 + p1;
-                  pk[e] = pack_half2(p0, p1);
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e]), p.scale_log2, -m_used);
+              const float x1 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used);
+              if constexpr (POLY) {
+                if (e & 1) {
+                  pk[e] = ex2_poly_h2(x0, x1);   // FMA pipe, half2 (row sums come from the ones row of V^T)
+                  continue;
                 }
-                const uint32_t q = static_cast<uint32_t>(c2 * 4 + q4);   // 16-byte piece inside the 64-key chunk
-                st_shared_v4(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
               }
+              const float p0 = ex2_approx(x0);
+              const float p1 = ex2_approx(x1);
+              if constexpr (!ONES) rsp[e & 1] += p0 + p1;
+              pk[e] = pack_half2(p0, p1);
             }
+            const uint32_t col8 = c * 4 + q4;   // 8-column piece index inside the BKV tile
+            const uint32_t cc = col8 >> 3, q = col8 & 7u;
+            st_shared_v4(prow + cc * (ATT_BQ * 128) + ((q ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
-          fence_proxy_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[cc]);
         }
       };
       if (ONES && poly)
@@ -368,9 +343,13 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       else
         exp_tile(std::false_type{});
       if constexpr (!ONES) l_sum += rsp[0] + rsp[1];
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
     }
     // ---- epilogue: O / l ----
-    mbar_wait(&pv_done[NPC - 1], static_cast<uint32_t>((n_tiles - 1) & 1));
+    mbar_wait(pv_done, static_cast<uint32_t>((n_tiles - 1) & 1));
     tc_fence_after();
     float inv;
     if constexpr (ONES) {

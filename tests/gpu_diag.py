@@ -424,15 +424,19 @@ def ncu_gemm2():
 
 
 def ncu_attn():
+    """L0 self-attention as the engine launches it (d = 40, ones-row V^T) for an ncu capture."""
     nimg, l, heads, d = 2, 9216, 8, 40
     C_ = heads * d
+    dp = d + 8
     q = rnd(nimg * l, C_).to(F16)
     k = rnd(nimg * l, C_, seed=11).to(F16)
-    vt = rnd(nimg, C_, l, seed=12).to(F16)
+    vt = torch.ones(nimg, heads, dp, l, dtype=F16, device=DEV)
+    vt[:, :, :d] = rnd(nimg, heads, d, l, seed=12).to(F16)
+    vt = vt.reshape(nimg, heads * dp, l)
     out = torch.empty_like(q)
     warm_gpu(1.0)
     for _ in range(2):
-        ops.attention(q, k, vt, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out)
+        ops.attention(q, k, vt, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out, vt_head_rows=dp, vt_ones=True)
     torch.cuda.synchronize()
     return True
 

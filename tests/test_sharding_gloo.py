@@ -124,11 +124,11 @@ def _worker_a2a(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_frame_pixel_exchange_world2_gloo():
+@pytest.mark.parametrize("world", [2, 4])
+def test_frame_pixel_exchange_gloo(world):
     """frames_to_pixels / pixels_to_frames (the two all-to-alls of a frame-sharded motion module):
     every rank ends up with ALL frames of its pixel slice in window order, and the round trip is the
     identity — including pixel counts that do not divide by the GPU count."""
-    world = 2
     port = 31500 + (os.getpid() % 2000)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -138,7 +138,7 @@ def test_frame_pixel_exchange_world2_gloo():
     out = [q.get(timeout=120) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(r for r, _ in out) == [0, 1]
+    assert sorted(r for r, _ in out) == list(range(world))
     for _, res in out:
         for hw, ok_fwd, ok_rt in res:
             assert ok_fwd, f"frames_to_pixels misplaced rows (hw={hw})"
