@@ -151,16 +151,41 @@ def build_model(cfg, dev):
     return model.to(device=dev, dtype=torch.float16).eval()
 
 
-def cpu_reference_sample(h, steps_cfg, reps, warm, budget_s=150.0):
+def host_threads():
+    """Threads the CPU arm may use: the affinity mask capped by the cgroup CPU quota (an oversubscribed
+    OpenMP pool on a quota-limited container collapses: measured 4.5 GFLOP/s with 128 threads), <= 64."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                parts = f.read().split()
+            if path.endswith("cpu.max"):
+                if parts[0] != "max":
+                    n = min(n, max(1, int(int(parts[0]) / int(parts[1]))))
+            else:
+                q = int(parts[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f2:
+                        n = min(n, max(1, q // int(f2.read().split()[0])))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, min(n, 64))
+
+
+def cpu_reference_sample(h, steps_cfg, reps, warm, budget_s=20.0):
     """The reference algorithm (fp32 oracle restating the reference modules) on the host cores.
-    Bounded sample: ONE frame (both CFG branches = 2 images) of one UNet forward.  The sample runs at
-    the config's latent size when (reps + warm) of them fit the time budget (predicted from a 32x32
-    calibration forward and the algorithmic FLOP ratio); otherwise at the largest of 64/48/32 that
-    fits, and the result is scaled by the algorithmic-FLOP ratio (stated in `sample`).  A clip step
-    costs `frames` such samples, the clip `num_steps * frames`."""
+    Bounded sample: ONE frame (both CFG branches = 2 images) of one UNet forward, at the largest latent
+    size of {config size, 64, 48, 32, 24, 16, 8} for which (reps + warm) forwards fit `budget_s` seconds
+    (predicted from an 8x8 calibration forward by the algorithmic-FLOP ratio); the result is scaled to
+    the config's size by the same ratio (stated in `sample`).  The loop also stops early once
+    2 x budget_s have elapsed.  A clip step costs `frames` such samples, the clip `num_steps * frames`."""
     from mikudance_b200 import synth
     from oracle import unet3d_oracle as O
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     cfg = synth.SD15_CONFIG
     sd = {k: v.float() for k, v in synth.synthetic_state_dict(cfg, seed=0).items()}
@@ -173,19 +198,26 @@ def cpu_reference_sample(h, steps_cfg, reps, warm, budget_s=150.0):
             O.unet3d_forward(sd, cfg, x, 499, ctx, banks=banks, cfg_guidance=True)
             return time.perf_counter() - t0
 
-    fl = {hs: sum(per_image_flops(hs, 1).values()) for hs in {h, 64, 48, 32}}
-    run(32)
-    t32 = run(32)
-    hs = 32
-    for cand in sorted({h, 64, 48, 32}, reverse=True):
-        if cand <= h and (reps + warm) * t32 * fl[cand] / fl[32] <= budget_s:
+    sizes = sorted({s_ for s_ in (h, 64, 48, 32, 24, 16, 8) if s_ <= h}, reverse=True)
+    fl = {hs: sum(per_image_flops(hs, 1).values()) for hs in sizes}
+    t_start = time.perf_counter()
+    t8 = run(8)                                        # calibration (also warms the thread pool)
+    hs = 8
+    for cand in sizes:
+        if (reps + warm) * t8 * fl[cand] / fl[8] <= budget_s:
             hs = cand
             break
-    times = [run(hs) for _ in range(warm + reps)][warm:]
+    times = []
+    for i in range(warm + reps):
+        dt = run(hs)
+        if i >= warm:
+            times.append(dt)
+        if time.perf_counter() - t_start > 2.0 * budget_s and times:
+            break
     t = sum(times) / len(times) * fl[h] / fl[hs]      # seconds for 2 images at the config's size
     fps = 1.0 / (steps_cfg * t)                        # frames / (steps * frames * t)
-    note = (f"latent {hs}x{hs}" + ("" if hs == h else f" scaled to {h}x{h} by algorithmic FLOPs "
-                                                       f"x{fl[h] / fl[hs]:.2f}"))
+    note = (f"latent {hs}x{hs}, {len(times)} timed forward(s), {cores} threads"
+            + ("" if hs == h else f", scaled to {h}x{h} by algorithmic FLOPs x{fl[h] / fl[hs]:.2f}"))
     return t, fps, cores, note
 
 
@@ -230,7 +262,7 @@ def main():
         if rank != 0:
             return
         reps = max(1, args.steps)
-        t, fps, cores, note = cpu_reference_sample(h, num_steps, reps, max(0, min(args.warmup, 1)))
+        t, fps, cores, note = cpu_reference_sample(h, num_steps, reps, max(0, min(args.warmup, 1)), budget_s=90.0)
         line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
                     warmup=args.warmup, ms_per_step=t * F_ * 1e3, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="f32", data="synthetic", impl="reference", config=workload,
@@ -354,7 +386,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        t, fps, cores, note = cpu_reference_sample(h, num_steps, 1, 0, budget_s=40.0)
+        t, fps, cores, note = cpu_reference_sample(h, num_steps, 1, 0, budget_s=15.0)
         cpu = dict(value=fps, unit="frames/s", cores=cores, kind="port",
                    sample=f"1 of {F_} frames (2 CFG images) of one config-{args.config} UNet forward "
                           f"({note}; {t:.1f} s), fp32 oracle restating the reference modules; "
