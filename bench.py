@@ -373,11 +373,14 @@ def main():
         kernels = prof.summary()
         shapes = prof.shapes(24)
         g = kernels.get("gemm_tc")
+        tr = ncu_traffic("gemm_tc_kernel")
         if g and g["ms"] > 0:
             ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
             roofline = dict(kernel="gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv, all launches of one step)",
                             bound="tensor", achieved=ach, peak=peaks["tflops_sustained"], unit="TFLOP/s",
-                            frac=ach / peaks["tflops_sustained"], traffic=ncu_traffic("gemm_tc_kernel"),
+                            frac=ach / peaks["tflops_sustained"],
+                            traffic=(tr["bytes_per_launch"] if tr else None), traffic_detail=tr,
+                            algorithmic_bytes_per_launch=g["bytes"] / g["n"],
                             launches=g["n"], share_of_step=g["ms"] / sum(k["ms"] for k in kernels.values()),
                             peak_source=peaks["source"] + ", sustained bf16 GEMM")
     step_tflop = frame_evals * 2 * sum(per_image_flops(h, min(F_, ctx_frames)).values()) / 1e12 \
