@@ -255,6 +255,43 @@ int mdk_cfg_ddim_step(mdk_ctx* ctx, const float* acc, const float* counter, void
                       const float* coef, float guidance_scale, int32_t nb, int32_t c, int32_t f,
                       int32_t hw, int32_t v_prediction, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Reference UNet (the "writer" that produces the feature banks). It is the
+ * SD-1.5 2-D UNet, so it runs on mdk_gemm_f16 / mdk_groupnorm_f16 / mdk_layernorm_f16 /
+ * mdk_attn_fwd_f16 above; only the three ops below are specific to it.
+ *
+ * mdk_cond_to_nhwc_f16 — channel slice of the NCHW condition latents, zero-padded NHWC, optionally
+ *   nearest-resized. Replaces `sample[:, :-2]`, `sample[:, -2:]` (src/models/unet_2d_mix.py:1208-1209)
+ *   and F.interpolate(motion_map, size=x.size()[2:], mode="nearest") (src/models/man_module.py:28).
+ *   x: [nimg, ctot, h, w] fp16; out: [nimg, ho, wo, cpad] fp16 holding channels
+ *   [c_first, c_first + c) sampled at (floor(oy*h/ho), floor(ox*w/wo)); columns >= c are zero.
+ * mdk_relu_f16 — in-place ReLU over n fp16 values (n % 8 == 0): MANModule.mlp_shared's activation
+ *   (src/models/man_module.py:18-20).
+ * mdk_man_modulate_f16 — MANModule.forward's normalisation and modulation
+ *   (src/models/man_module.py:26,32): parameter-free InstanceNorm2d (per image and channel over the hw
+ *   pixels, biased variance) followed by  out = normalized * (1 + gamma) + beta.
+ *   x, out: [nimg, hw, c] fp16; gb: [nimg*hw, ldgb] fp16 with gamma in columns [0, c) and beta in
+ *   [c, 2c) (the fused mlp_gamma | mlp_beta convolution output); ws: mdk_man_ws_bytes(nimg, c) bytes.
+ *   Deterministic (per-CTA partial sums, fixed-order fp64 combine, no atomics).
+ */
+int mdk_cond_to_nhwc_f16(mdk_ctx* ctx, const void* x, void* out, int32_t nimg, int32_t ctot,
+                         int32_t c_first, int32_t c, int32_t h, int32_t w, int32_t ho, int32_t wo,
+                         int32_t cpad, void* stream);
+int mdk_relu_f16(mdk_ctx* ctx, void* x, int64_t n, void* stream);
+
+typedef struct {
+  const void* x;
+  const void* gb;
+  int64_t ldgb;
+  int32_t nimg, hw, c;
+  float eps;
+  void* out;
+  void* ws;
+} mdk_man_args;
+
+int64_t mdk_man_ws_bytes(int32_t nimg, int32_t c);
+int mdk_man_modulate_f16(mdk_ctx* ctx, const mdk_man_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,14 @@ class TembArgs(C.Structure):
     ]
 
 
+class ManArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("gb", c_void_p), ("ldgb", c_int64),
+        ("nimg", c_int32), ("hw", c_int32), ("c", c_int32), ("eps", c_float),
+        ("out", c_void_p), ("ws", c_void_p),
+    ]
+
+
 # every symbol include/mdk.h declares (tests check the library exports all of them)
 EXPORTS = [
     "mdk_create", "mdk_destroy", "mdk_last_error", "mdk_abi_version", "mdk_launch_count",
@@ -93,6 +101,7 @@ EXPORTS = [
     "mdk_groupnorm_ws_bytes", "mdk_groupnorm_f16", "mdk_layernorm_f16", "mdk_upsample2x_f16",
     "mdk_im2col3x3_f16", "mdk_time_embed_f16", "mdk_latents_to_nhwc", "mdk_pred_accumulate",
     "mdk_cfg_ddim_step",
+    "mdk_cond_to_nhwc_f16", "mdk_relu_f16", "mdk_man_ws_bytes", "mdk_man_modulate_f16",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -134,6 +143,12 @@ def load_library() -> C.CDLL:
                                         c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p]
     lib.mdk_cfg_ddim_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                       c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.mdk_cond_to_nhwc_f16.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int32] * 9 + [c_void_p]
+    lib.mdk_relu_f16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    lib.mdk_man_ws_bytes.restype = c_int64
+    lib.mdk_man_ws_bytes.argtypes = [c_int32, c_int32]
+    lib.mdk_man_modulate_f16.argtypes = [c_void_p, C.POINTER(ManArgs), c_void_p]
+    lib.mdk_man_modulate_f16.restype = C.c_int
     _lib = lib
     return lib
 

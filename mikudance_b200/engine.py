@@ -61,8 +61,6 @@ class _Resnet:
 
 class UNetEngine:
     def __init__(self, model):
-        from ._lib import load_library
-        self.model = model
         p = next(model.parameters())
         if not p.is_cuda:
             raise RuntimeError("UNetEngine: the model must live on a CUDA (sm_100a) device; "
@@ -70,13 +68,18 @@ class UNetEngine:
         if p.dtype != F16:
             raise RuntimeError(f"UNetEngine: weights must be float16 (got {p.dtype}); call "
                                ".to(dtype=torch.float16) like scripts/inference_video.py does")
-        self.dev = p.device
+        self._setup(model, p.device)
+
+    def _setup(self, model, dev):
+        self.model = model
+        self.dev = dev
         self.cfg = model._plan_cfg
         self.plan = block_plan(self.cfg)
         self.groups = self.cfg["norm_num_groups"]
         self.eps = self.cfg["norm_eps"]
         self.heads = self.cfg["attention_head_dim"]
         self.mheads = self.cfg["motion_heads"]
+        from ._lib import load_library
         self.geglu_block = int(load_library().mdk_gemm_geglu_block())
         self.trace = None       # optional {stage: (tensor, N, h, w)} of intermediate activations (tests)
         self.pg = None          # torch.distributed process group for frame sharding
@@ -246,7 +249,8 @@ class UNetEngine:
         g = ops.gemm(n, o.ff1_w, bias=o.ff1_b, geglu=True)
         return ops.gemm(g, o.ff2_w, bias=o.ff2_b, residual=h)
 
-    def _spatial(self, s, x, N, H, W, f, ctx2d, nctx, lctx, bank, n_uncond):
+    def _spatial(self, s, x, N, H, W, f, ctx2d, nctx, lctx, bank, n_uncond, capture=None):
+        """`capture` (reference UNet, write mode): dict that receives norm1's output under s.name."""
         hw = H * W
         C = s.c
         d = C // self.heads
@@ -275,6 +279,8 @@ class UNetEngine:
                      trans_head=th)
         else:
             n1 = ops.layernorm(h, s.ln1w, s.ln1b)
+            if capture is not None:
+                capture[s.name] = n1
             ops.gemm(n1, s.wqkv, outs=[q, k, vt], trans=[False, False, True], trans_rows=hw, trans_head=th)
         a = ops.attention(q, k, vt, nimg=N, lq=hw, lkv=hw, heads=self.heads, d=d, vt_head_rows=dp,
                           vt_ones=ones)

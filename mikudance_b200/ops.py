@@ -10,7 +10,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (AttnArgs, GemmArgs, GnArgs, LnArgs, TattnArgs, TembArgs, check, cur_stream,
+from ._lib import (AttnArgs, GemmArgs, GnArgs, LnArgs, ManArgs, TattnArgs, TembArgs, check, cur_stream,
                    get_ctx, load_library, ptr)
 
 F16 = torch.float16
@@ -343,3 +343,47 @@ def cfg_ddim_step(acc: torch.Tensor, counter: torch.Tensor, latents: torch.Tenso
                                                   ptr(latents), ptr(coef), float(guidance_scale), nb, c,
                                                   F, h * w, 1 if v_prediction else 0,
                                                   cur_stream(acc.device)), "mdk_cfg_ddim_step")
+
+
+# ------------------------------------------------------------------------------------------------
+# reference UNet (writer) only — SURVEY.md §8f row 1
+# ------------------------------------------------------------------------------------------------
+def cond_to_nhwc(x: torch.Tensor, *, c_first: int, c: int, ho: int, wo: int, cpad: int) -> torch.Tensor:
+    """x [nimg, ctot, h, w] fp16 NCHW -> [(nimg ho wo), cpad] fp16: channels [c_first, c_first+c),
+    nearest-resized to (ho, wo), zero-padded to cpad columns."""
+    _chk16(x, "x")
+    assert x.dim() == 4 and x.is_contiguous()
+    nimg, ctot, h, w = x.shape
+    out = torch.empty((nimg * ho * wo, cpad), dtype=F16, device=x.device)
+    _run("cond_glue", 0.0, 2.0 * (nimg * h * w * c + out.numel()),
+         lambda: load_library().mdk_cond_to_nhwc_f16(get_ctx(x.device), ptr(x), ptr(out), nimg, ctot,
+                                                     c_first, c, h, w, ho, wo, cpad,
+                                                     cur_stream(x.device)), "mdk_cond_to_nhwc_f16")
+    return out
+
+
+def relu_(x: torch.Tensor) -> torch.Tensor:
+    _chk16(x, "x")
+    assert x.is_contiguous()
+    _run("relu", 0.0, 4.0 * x.numel(),
+         lambda: load_library().mdk_relu_f16(get_ctx(x.device), ptr(x), x.numel(), cur_stream(x.device)),
+         "mdk_relu_f16")
+    return x
+
+
+def man_modulate(x: torch.Tensor, gb: torch.Tensor, *, nimg: int, hw: int, eps: float = 1e-5) -> torch.Tensor:
+    """x [(nimg hw), C]; gb [(nimg hw), 2C] = gamma | beta -> InstanceNorm(x) * (1 + gamma) + beta"""
+    _chk16(x, "x"), _chk16(gb, "gb")
+    c = x.shape[1]
+    assert x.is_contiguous() and x.shape[0] == nimg * hw and gb.shape == (nimg * hw, 2 * c)
+    dev = x.device
+    out = torch.empty_like(x)
+    ws = torch.empty((load_library().mdk_man_ws_bytes(nimg, c),), dtype=torch.uint8, device=dev)
+    a = ManArgs()
+    a.x, a.gb, a.ldgb = ptr(x), ptr(gb), gb.stride(0)
+    a.nimg, a.hw, a.c, a.eps = nimg, hw, c, eps
+    a.out, a.ws = ptr(out), ptr(ws)
+    _run("man_modulate", 0.0, 10.0 * nimg * hw * c,
+         lambda: load_library().mdk_man_modulate_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
+         "mdk_man_modulate_f16")
+    return out

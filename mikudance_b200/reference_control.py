@@ -43,7 +43,9 @@ class ReferenceAttentionControl:
                 module.bank = []                                   # :314
                 module.attn_weight = float(i) / float(len(mods))   # :315
             if hasattr(unet, "_ref_control"):
-                unet._ref_control = dict(mode=mode, fusion_blocks=fusion_blocks,
+                # `blocks`: the hooked transformer blocks — in write mode the reference UNet appends
+                # norm1(hidden_states) to exactly these blocks' banks (mutual_mix_attention.py:139-140)
+                unet._ref_control = dict(mode=mode, fusion_blocks=fusion_blocks, blocks=mods,
                                          do_classifier_free_guidance=do_classifier_free_guidance)
                 if fusion_blocks != "full" and mode == "read":
                     # "midup": only mid/up blocks read banks; the others keep empty banks, which the

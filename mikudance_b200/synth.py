@@ -60,8 +60,15 @@ def positional_encoding(max_len: int, d_model: int) -> torch.Tensor:
     return pe
 
 
-def state_dict_spec(cfg) -> List[Tuple[str, Tuple[int, ...], str]]:
-    """[(key, shape, kind)] for every tensor of the reference UNet3DConditionModel state dict.
+REF_CHAR_CHANNELS = 20     # reference UNet conv_in: in_channels * 5   (src/models/unet_2d_mix.py:320-327)
+REF_MOTION_CHANNELS = 2    # scene-motion map, sample[:, -2:]          (src/models/unet_2d_mix.py:1208-1209)
+MAN_HIDDEN = 128           # src/models/man_module.py:14-15
+
+
+def state_dict_spec(cfg, reference_unet: bool = False) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """[(key, shape, kind)] for every tensor of the reference UNet3DConditionModel state dict, or — with
+    reference_unet=True — of the 2-D reference UNet (src/models/unet_2d_mix.py: 20-channel conv_in, one
+    MANModule per down block, no motion modules, no conv_norm_out / conv_out).
     kind: 'w' weight (fan-in = prod(shape[1:])), 'b' bias, 'g' norm gain, 'pe' buffer."""
     boc = cfg["block_out_channels"]
     c0 = boc[0]
@@ -126,7 +133,10 @@ def state_dict_spec(cfg) -> List[Tuple[str, Tuple[int, ...], str]]:
         norm(b + ".ff_norm", c)
         lin(t + ".proj_out", c, c)
 
-    conv("conv_in", c0, cfg["in_channels"], 3)
+    if reference_unet:
+        def motion(p, c):  # noqa: F811 — the 2-D reference UNet has no motion modules
+            return None
+    conv("conv_in", c0, REF_CHAR_CHANNELS if reference_unet else cfg["in_channels"], 3)
     lin("time_embedding.linear_1", temb, c0)
     lin("time_embedding.linear_2", temb, temb)
     plan = block_plan(cfg)
@@ -139,6 +149,11 @@ def state_dict_spec(cfg) -> List[Tuple[str, Tuple[int, ...], str]]:
             motion(f"{p}.motion_modules.{j}", d["out_c"])
         if d["downsample"]:
             conv(f"{p}.downsamplers.0.conv", d["out_c"], d["out_c"], 3)
+        if reference_unet:                                  # src/models/unet_2d_mix.py:556-557
+            m = f"man_blocks.{d['idx']}"
+            conv(m + ".mlp_shared.0", MAN_HIDDEN, REF_MOTION_CHANNELS, 3)
+            conv(m + ".mlp_gamma", d["out_c"], MAN_HIDDEN, 3)
+            conv(m + ".mlp_beta", d["out_c"], MAN_HIDDEN, 3)
     mc = plan["mid_c"]
     resnet("mid_block.resnets.0", mc, mc)
     spatial("mid_block.attentions.0", mc)
@@ -153,8 +168,9 @@ def state_dict_spec(cfg) -> List[Tuple[str, Tuple[int, ...], str]]:
             motion(f"{p}.motion_modules.{j}", u["out_c"])
         if u["upsample"]:
             conv(f"{p}.upsamplers.0.conv", u["out_c"], u["out_c"], 3)
-    norm("conv_norm_out", c0)
-    conv("conv_out", cfg["out_channels"], c0, 3)
+    if not reference_unet:
+        norm("conv_norm_out", c0)
+        conv("conv_out", cfg["out_channels"], c0, 3)
     return spec
 
 
@@ -164,10 +180,11 @@ def _seeded_randn(name: str, shape, seed: int) -> torch.Tensor:
     return torch.randn(shape, generator=g, dtype=torch.float32)
 
 
-def synthetic_state_dict(cfg, seed: int = 0, dtype=torch.float16) -> Dict[str, torch.Tensor]:
+def synthetic_state_dict(cfg, seed: int = 0, dtype=torch.float16,
+                         reference_unet: bool = False) -> Dict[str, torch.Tensor]:
     """Deterministic random-init weights with the reference's key set (values rounded to `dtype`)."""
     sd = {}
-    for name, shape, kind in state_dict_spec(cfg):
+    for name, shape, kind in state_dict_spec(cfg, reference_unet):
         if kind == "w":
             fan_in = 1
             for s in shape[1:]:
@@ -223,3 +240,14 @@ def synthetic_inputs(cfg, b: int, f: int, h: int, w: int, lctx: int = 257, seed:
     if b == 2:
         ctx = torch.cat([torch.zeros_like(ctx), ctx], dim=0)
     return sample, ctx
+
+
+def synthetic_reference_inputs(cfg, n_img: int, h: int, w: int, lctx: int = 257, seed: int = 200):
+    """Inputs of the reference UNet (src/pipelines/pipeline_mikudance.py:634-653): condition latents
+    [n_img, 22, h, w] (ref / skeleton / pose / face / hand latents + 2 scene-motion channels) and the
+    TILED context [n_img, lctx, ctx_dim] = [uncond(zeros), cond, uncond, cond, …] (:645)."""
+    x = _seeded_randn("ref_latents", (n_img, REF_CHAR_CHANNELS + REF_MOTION_CHANNELS, h, w), seed)
+    c = _seeded_randn("ref_ctx", (1, lctx, cfg["cross_attention_dim"]), seed + 1)
+    pair = torch.cat([torch.zeros_like(c), c], dim=0)
+    ctx = pair.repeat((n_img + 1) // 2, 1, 1)[:n_img]
+    return x, ctx

@@ -99,3 +99,11 @@ class Attention(nn.Module):
                 **cross_attention_kwargs):
         return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
                               attention_mask=attention_mask, **cross_attention_kwargs)
+
+
+class AttnAddedKVProcessor:  # names imported by the reference's unet_2d_mix.py; unused for SD-1.5
+    pass
+
+
+ADDED_KV_ATTENTION_PROCESSORS = (AttnAddedKVProcessor,)
+CROSS_ATTENTION_PROCESSORS = (AttnProcessor, AttnProcessor2_0)

@@ -36,8 +36,11 @@ class Timesteps(nn.Module):
 
 
 class TimestepEmbedding(nn.Module):
-    def __init__(self, in_channels, time_embed_dim, act_fn="silu", out_dim=None):
+    def __init__(self, in_channels, time_embed_dim, act_fn="silu", out_dim=None, post_act_fn=None,
+                 cond_proj_dim=None):
         super().__init__()
+        if post_act_fn is not None or cond_proj_dim is not None or act_fn not in ("silu", "swish"):
+            raise NotImplementedError("stand-in: only the SD-1.5 TimestepEmbedding options")
         self.linear_1 = nn.Linear(in_channels, time_embed_dim)
         self.act = nn.SiLU()
         self.linear_2 = nn.Linear(time_embed_dim, out_dim if out_dim is not None else time_embed_dim)
@@ -50,3 +53,16 @@ class SinusoidalPositionalEmbedding(nn.Module):  # imported by the reference, ne
     def __init__(self, *a, **k):
         super().__init__()
         raise NotImplementedError("stand-in: not on the hot path")
+
+
+def _unused(name):
+    def __init__(self, *a, **k):
+        nn.Module.__init__(self)
+        raise NotImplementedError(f"stand-in: {name} is not on the SD-1.5 path")
+    return type(name, (nn.Module,), {"__init__": __init__})
+
+
+for _n in ("GaussianFourierProjection", "ImageHintTimeEmbedding", "ImageProjection", "ImageTimeEmbedding",
+           "PositionNet", "TextImageProjection", "TextImageTimeEmbedding", "TextTimeEmbedding",
+           "CaptionProjection"):
+    globals()[_n] = _unused(_n)

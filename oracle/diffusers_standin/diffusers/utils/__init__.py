@@ -35,3 +35,26 @@ class _Logging:
 
 
 logging = _Logging()
+
+USE_PEFT_BACKEND = False
+
+
+def deprecate(*args, **kwargs):
+    return None
+
+
+def scale_lora_layers(model, weight):
+    return None
+
+
+def unscale_lora_layers(model, weight=None):
+    return None
+
+
+def is_torch_version(op, version):
+    import operator
+
+    import torch
+    from packaging.version import parse
+    ops = {">": operator.gt, ">=": operator.ge, "==": operator.eq, "<": operator.lt, "<=": operator.le}
+    return ops[op](parse(parse(torch.__version__).base_version), parse(version))

@@ -8,6 +8,11 @@ What comes from where:
                            `ReferenceAttentionControl(mode="read")` (src/models/unet_3d_mix.py,
                            src/models/mutual_mix_attention.py) imported from /root/reference through
                            oracle/diffusers_standin, fp32 CPU, on mikudance_b200.synth inputs/weights.
+  * refunet_tiny.npz     — the reference's unmodified 2-D reference UNet (src/models/unet_2d_mix.py +
+                           man_module.py) under ReferenceAttentionControl(mode="write"): its output
+                           sample, four of the sixteen feature banks in full and the L2 norm / mean of all
+                           sixteen (in the writer/reader pairing order); refunet_state_dict_sd15.json is
+                           its key -> shape contract at the SD-1.5 size.
   * context_windows.json — outputs of the reference's src/pipelines/context.py (imports untouched).
   * state_dict_sd15.json — key -> shape of the reference model built with the SD-1.5 config +
                            configs/inference/mikudance_config.yaml (the weight-container contract).
@@ -55,6 +60,32 @@ def install_banks(model, banks, cfg, do_cfg):
         mod.bank = [banks[name].clone()] if banks is not None else []
 
 
+REFUNET_FULL_BANKS = ("down_blocks.0.attentions.0", "up_blocks.1.attentions.2", "mid_block.attentions.0",
+                      "up_blocks.3.attentions.2")
+
+
+def build_reference_refunet(cfg):
+    from src.models.unet_2d_mix import UNet2DConditionModel  # the reference's class
+    return UNet2DConditionModel(block_out_channels=cfg["block_out_channels"],
+                                cross_attention_dim=cfg["cross_attention_dim"]).eval()
+
+
+def run_reference_refunet(model, x, ctx, cfg):
+    """-> (sample, {attention path: bank}) of the reference writer, banks keyed in pairing order."""
+    from src.models.attention import BasicTransformerBlock
+    from src.models.mutual_mix_attention import ReferenceAttentionControl, torch_dfs
+    from mikudance_b200 import synth
+    writer = ReferenceAttentionControl(model, mode="write", do_classifier_free_guidance=True,
+                                       fusion_blocks="full", batch_size=1)
+    with torch.no_grad():
+        y = model(x, torch.zeros((), dtype=torch.int64), encoder_hidden_states=ctx, return_dict=False)[0]
+    mods = [m for m in torch_dfs(model) if isinstance(m, BasicTransformerBlock)]
+    mods = sorted(mods, key=lambda m: -m.norm1.normalized_shape[0])
+    banks = {name: mod.bank[0].clone() for mod, (name, c, ds) in zip(mods, synth.reader_bank_order(cfg))}
+    writer.clear()
+    return y, banks
+
+
 def main():
     from mikudance_b200 import synth
     os.makedirs(OUT, exist_ok=True)
@@ -75,6 +106,28 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), y=y.numpy().astype(np.float32),
                             meta=np.array([B, f, h, w, lctx, t, int(with_banks)]))
         print(name, tuple(y.shape), float(y.abs().mean()))
+
+    # reference UNet (writer)
+    ref = build_reference_refunet(cfg)
+    rsd = {k: v.float() for k, v in synth.synthetic_state_dict(cfg, seed=0, reference_unet=True).items()}
+    ref.load_state_dict(rsd)
+    N, h, w, lctx = 2, 24, 24, 7
+    x, ctx = synth.synthetic_reference_inputs(cfg, N, h, w, lctx=lctx)
+    x, ctx = x.half().float(), ctx.half().float()
+    y, banks = run_reference_refunet(ref, x, ctx, cfg)
+    order = [n for n, _, _ in synth.reader_bank_order(cfg)]
+    np.savez_compressed(
+        os.path.join(OUT, "refunet_tiny.npz"), y=y.numpy().astype(np.float32),
+        meta=np.array([N, h, w, lctx]),
+        bank_norm=np.array([float(banks[n].norm()) for n in order], dtype=np.float64),
+        bank_mean=np.array([float(banks[n].double().mean()) for n in order], dtype=np.float64),
+        **{"bank_" + n.replace(".", "_"): banks[n].numpy().astype(np.float32) for n in REFUNET_FULL_BANKS})
+    print("refunet_tiny", tuple(y.shape), float(y.abs().mean()), len(banks))
+    bigref = build_reference_refunet(synth.SD15_CONFIG)
+    rshapes = {k: list(v.shape) for k, v in bigref.state_dict().items()}
+    json.dump(rshapes, open(os.path.join(OUT, "refunet_state_dict_sd15.json"), "w"), indent=0)
+    print("reference-unet sd15 tensors", len(rshapes), "params", sum(int(np.prod(s)) for s in rshapes.values()))
+    del bigref
 
     spec = importlib.util.spec_from_file_location("refctx", os.path.join(REF, "src/pipelines/context.py"))
     refctx = importlib.util.module_from_spec(spec)

@@ -584,7 +584,90 @@ def check_unet_a():
     return unet_check(synth.SD15_CONFIG, 2, 4, 32, 32, 257, 499, True, "cfgA")
 
 
+# ------------------------------------------------------------------------------------------------
+# reference UNet (writer) — SURVEY.md §8f row 1
+# ------------------------------------------------------------------------------------------------
+def check_refunet_ops():
+    """cond_to_nhwc / relu / man_modulate against plain PyTorch on the same inputs."""
+    import torch.nn.functional as Fn
+    ok = True
+    for (n, h, w, ho, wo) in [(3, 16, 24, 16, 24), (2, 32, 32, 4, 4), (5, 16, 16, 2, 2), (2, 24, 40, 12, 20)]:
+        x = rnd(n, 22, h, w, seed=n * 100 + ho).to(F16)
+        char = ops.cond_to_nhwc(x, c_first=0, c=20, ho=ho, wo=wo, cpad=24)
+        mot = ops.cond_to_nhwc(x, c_first=20, c=2, ho=ho, wo=wo, cpad=8)
+        torch.cuda.synchronize()
+        rc = Fn.interpolate(x[:, :20].float(), size=(ho, wo), mode="nearest").permute(0, 2, 3, 1).reshape(-1, 20)
+        rm = Fn.interpolate(x[:, 20:].float(), size=(ho, wo), mode="nearest").permute(0, 2, 3, 1).reshape(-1, 2)
+        ok &= bool(torch.equal(char[:, :20].float(), rc)) and bool((char[:, 20:] == 0).all())
+        ok &= bool(torch.equal(mot[:, :2].float(), rm)) and bool((mot[:, 2:] == 0).all())
+        print(f"[{'OK ' if ok else 'BAD'}] cond_to_nhwc n={n} {h}x{w}->{ho}x{wo} (exact)")
+    a = rnd(1000, 128, seed=3).to(F16)
+    ref = torch.relu(a.float())
+    ops.relu_(a)
+    torch.cuda.synchronize()
+    e = bool(torch.equal(a.float(), ref))
+    print(f"[{'OK ' if e else 'BAD'}] relu (exact)")
+    ok &= e
+    for (n, hw, c) in [(2, 1024, 64), (3, 144, 320), (2, 36, 1280), (4, 9, 256), (1, 2304, 640), (2, 2, 128)]:
+        x = (rnd(n * hw, c, seed=c + hw) * 1.7 + 0.3).to(F16)
+        gb = rnd(n * hw, 2 * c, seed=c + hw + 1, scale=0.5).to(F16)
+        out = ops.man_modulate(x, gb, nimg=n, hw=hw)
+        out2 = ops.man_modulate(x, gb, nimg=n, hw=hw)
+        torch.cuda.synchronize()
+        xi = x.float().view(n, hw, c).permute(0, 2, 1)
+        nrm = Fn.instance_norm(xi.unsqueeze(-1), eps=1e-5).squeeze(-1).permute(0, 2, 1).reshape(n * hw, c)
+        ref = nrm * (1 + gb.float()[:, :c]) + gb.float()[:, c:]
+        ok &= report(f"man_modulate n={n} hw={hw} c={c}", out, ref)
+        ok &= bool(torch.equal(out, out2))          # deterministic: no atomics
+    return ok
+
+
+def build_refunet(cfg, seed=0):
+    from mikudance_b200 import synth
+    from mikudance_b200.unet_2d_ref import UNet2DConditionModel
+    m = UNet2DConditionModel(block_out_channels=cfg["block_out_channels"],
+                             cross_attention_dim=cfg["cross_attention_dim"])
+    sd = synth.synthetic_state_dict(cfg, seed=seed, reference_unet=True)
+    m.load_state_dict(sd)
+    return m.to(device=DEV, dtype=F16).eval(), sd
+
+
+def refunet_check(cfg, N, h, w, lctx, tag=""):
+    """native reference UNet in write mode vs the fp32 oracle: output sample and all sixteen banks."""
+    from mikudance_b200 import synth
+    from mikudance_b200.reference_control import ReferenceAttentionControl
+    from oracle import refunet_oracle as R
+    m, sd = build_refunet(cfg)
+    writer = ReferenceAttentionControl(m, mode="write", do_classifier_free_guidance=True, fusion_blocks="full")
+    x, ctx = synth.synthetic_reference_inputs(cfg, N, h, w, lctx=lctx)
+    y = m(x.to(DEV, F16), torch.zeros((), dtype=torch.int64, device=DEV),
+          encoder_hidden_states=ctx.to(DEV, F16), return_dict=False)[0]
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        yo, bo = R.refunet_forward({k: v.float() for k, v in sd.items()}, cfg, x.half().float(), 0,
+                                   ctx.half().float())
+    ok = report(f"{tag} refunet sample", y.cpu().reshape(-1, 1), yo.reshape(-1, 1), tol=5e-3)
+    for blk, (name, c, ds) in zip(writer._blocks(m), synth.reader_bank_order(cfg)):
+        assert len(blk.bank) == 1 and tuple(blk.bank[0].shape) == tuple(bo[name].shape)
+        ok &= report(f"{tag} bank {name}", blk.bank[0].cpu().reshape(-1, c), bo[name].reshape(-1, c), tol=5e-3)
+    return ok, m, writer
+
+
+def check_refunet_tiny():
+    from mikudance_b200 import synth
+    ok, _, _ = refunet_check(synth.TINY_CONFIG, 2, 32, 32, 7, "tiny")
+    ok2, _, _ = refunet_check(synth.TINY_CONFIG, 3, 16, 24, 257, "tiny-ragged")
+    return ok and ok2
+
+
+def check_refunet_a():
+    """SD-1.5 sized reference UNet at BASELINE config A's latent size (32x32), 4 frames x 2 branches."""
+    from mikudance_b200 import synth
+    return refunet_check(synth.SD15_CONFIG, 8, 32, 32, 257, "cfgA")[0]
+
+
 CHECKS = {
+    "refunet_ops": check_refunet_ops, "refunet_tiny": check_refunet_tiny, "refunet_a": check_refunet_a,
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
     "norms": check_norms, "temporal": check_temporal, "misc": check_misc, "attn": check_attn,

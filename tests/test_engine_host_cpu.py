@@ -1,0 +1,90 @@
+"""CPU: the product's HOST orchestration (UNetEngine / RefUNetEngine: weight packing, layouts, fused
+q|k|v and GEGLU panels, skip concat, bank add / bank capture, MAN wiring, PE row bias) against the
+oracle, with every kernel call routed to the CPU statement of its C-ABI contract
+(tests/ops_contract_cpu.py).  The kernels themselves are covered by the `-m gpu` tests."""
+import pytest
+import torch
+
+import ops_contract_cpu as K
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+def _unet3d(cfg):
+    from mikudance_b200.unet_3d import UNet3DConditionModel
+    return UNet3DConditionModel(block_out_channels=cfg["block_out_channels"],
+                                cross_attention_dim=cfg["cross_attention_dim"], use_inflated_groupnorm=True,
+                                use_motion_module=True, motion_module_mid_block=True,
+                                motion_module_type="Vanilla", unet_use_cross_frame_attention=False,
+                                unet_use_temporal_attention=False)
+
+
+@pytest.mark.parametrize("B,f,h,w,lctx,with_banks", [(2, 3, 16, 8, 9, True), (1, 2, 8, 8, 5, False)])
+def test_unet3d_engine_orchestration_matches_oracle(monkeypatch, B, f, h, w, lctx, with_banks):
+    from mikudance_b200 import synth
+    from mikudance_b200.engine import UNetEngine
+    from mikudance_b200.reference_control import ReferenceAttentionControl
+    from oracle import unet3d_oracle as O
+    K.install(monkeypatch)
+    cfg = synth.TINY_CONFIG
+    sd = synth.synthetic_state_dict(cfg, seed=1)
+    model = _unet3d(cfg)
+    model.load_state_dict(sd)
+    model = model.half().eval()
+    x, ctx = synth.synthetic_inputs(cfg, B, f, h, w, lctx=lctx)
+    banks = synth.synthetic_banks(cfg, B * f, h, w) if with_banks else None
+    ReferenceAttentionControl(model, mode="read", do_classifier_free_guidance=(B == 2), fusion_blocks="full")
+    if banks is not None:
+        for blk, (name, c, ds) in zip(model.spatial_blocks(), synth.reader_bank_order(cfg)):
+            blk.bank = [banks[name]]
+    eng = K.engine_on_cpu(UNetEngine, model)
+    y = eng.forward_api(x.half(), 499, ctx.half())
+    with torch.no_grad():
+        yo = O.unet3d_forward({k: v.float() for k, v in sd.items()}, cfg, x.half().float(), 499,
+                              ctx.half().float(), banks=banks, cfg_guidance=(B == 2))
+    assert y.shape == yo.shape
+    assert _rel(y, yo) < 5e-3          # fp16 storage between ops vs the fp32 oracle (GPU bar: same)
+
+
+def test_refunet_engine_orchestration_matches_oracle(monkeypatch):
+    from mikudance_b200 import synth
+    from mikudance_b200.engine_ref import RefUNetEngine
+    from mikudance_b200.reference_control import ReferenceAttentionControl
+    from mikudance_b200.unet_2d_ref import UNet2DConditionModel
+    from oracle import refunet_oracle as R
+    K.install(monkeypatch)
+    cfg = synth.TINY_CONFIG
+    sd = synth.synthetic_state_dict(cfg, seed=2, reference_unet=True)
+    model = UNet2DConditionModel(block_out_channels=cfg["block_out_channels"],
+                                 cross_attention_dim=cfg["cross_attention_dim"])
+    model.load_state_dict(sd)
+    model = model.half().eval()
+    writer = ReferenceAttentionControl(model, mode="write", do_classifier_free_guidance=True,
+                                       fusion_blocks="full")
+    # 32x32 latents: the deepest level still has 4x4 pixels (InstanceNorm over 1-2 pixels is ill-conditioned
+    # for ANY fp16 pipeline: the fp16-emulated reference path itself deviates by 9e-2 there)
+    N, h, w = 2, 32, 32
+    x, ctx = synth.synthetic_reference_inputs(cfg, N, h, w, lctx=7)
+    eng = K.engine_on_cpu(RefUNetEngine, model)
+    y, banks = eng.forward_api(x.half(), 0, ctx.half())
+    with torch.no_grad():
+        yo, bo = R.refunet_forward({k: v.float() for k, v in sd.items()}, cfg, x.half().float(), 0,
+                                   ctx.half().float())
+    assert set(banks) == set(bo) and len(banks) == 16
+    for name in bo:
+        assert banks[name].shape == bo[name].shape
+        assert _rel(banks[name], bo[name]) < 5e-3, name
+    assert _rel(y, yo) < 5e-3
+    # the writer contract: forward() appends [N, hw, C] to every hooked block's bank, in pairing order
+    model._engine = eng
+    monkeypatch.setattr(type(x), "is_cuda", property(lambda self: True), raising=False)
+    out = model(x.half(), torch.zeros((), dtype=torch.int64), encoder_hidden_states=ctx.half(),
+                return_dict=False)[0]
+    assert out.shape == (N, cfg["block_out_channels"][0], h, w)
+    for blk, (name, c, ds) in zip(writer._blocks(model), synth.reader_bank_order(cfg)):
+        assert len(blk.bank) == 1 and torch.equal(blk.bank[0], banks[name])
+        assert blk.bank[0].shape == (N, (h // ds) * (w // ds), c)
+    writer.clear()
+    assert all(len(b.bank) == 0 for b in writer._blocks(model))
