@@ -221,6 +221,39 @@ def cpu_reference_sample(h, steps_cfg, reps, warm, budget_s=20.0):
     return t, fps, cores, note
 
 
+def time_reference_unet(cfg, dev, h, f_win, n_windows, num_steps, ms_step):
+    """One forward of the native reference UNet (mikudance_b200.unet_2d_ref) on a
+    window's 2 x f_win images: random-init SD-1.5-size weights, synthetic condition latents, the tiled
+    [uncond, cond, ...] CLIP context.  CUDA events, 1 warm-up + 3 timed forwards."""
+    from mikudance_b200 import synth
+    from mikudance_b200.unet_2d_ref import UNet2DConditionModel
+    m = UNet2DConditionModel(block_out_channels=cfg["block_out_channels"],
+                             cross_attention_dim=cfg["cross_attention_dim"])
+    m.load_state_dict(synth.synthetic_state_dict(cfg, seed=0, reference_unet=True))
+    m = m.to(device=dev, dtype=torch.float16).eval()
+    n_img = 2 * f_win
+    x, ctx = synth.synthetic_reference_inputs(cfg, n_img, h, h, lctx=257)
+    x, ctx = x.to(dev, torch.float16), ctx.to(dev, torch.float16)
+    eng = m.engine()
+    eng.set_timestep(0)
+    eng.run(x, ctx)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        eng.run(x, ctx)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 3
+    clip_ms = num_steps * ms_step + n_windows * ms
+    del m, eng
+    torch.cuda.empty_cache()
+    return dict(ms_per_window=ms, images=n_img, windows=n_windows, hoisted=True,
+                share_of_clip=n_windows * ms / clip_ms,
+                note="runs once per context window per clip (its inputs are step-invariant); the reference "
+                     "runs it once per window per step")
+
+
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch (average over the launches of one step) from
     the committed ncu launch list of `bench.py --ncu-step` (profiles/r01_ncu_step_traffic.json, written by
@@ -244,6 +277,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-profile", action="store_true")
+    ap.add_argument("--skip-reference-unet", action="store_true",
+                    help="do not time the hoisted reference UNet (writer) forward that produces the banks")
     ap.add_argument("--ncu-step", action="store_true",
                     help="run ONE eager step inside a cudaProfilerStart/Stop range and exit "
                          "(for `ncu --profile-from-start off`; prints no bench line)")
@@ -387,6 +422,16 @@ def main():
         if cfg is synth.SD15_CONFIG else None
     step_ach = step_tflop / (ms_step * 1e-3) * 1.0 if step_tflop else None
 
+    # ---- the hoisted reference UNet (writer): once per context window per CLIP, not per step ----
+    # (outside the step metric; reported so the whole loop's cost is visible: the reference runs it every
+    # step for every window, src/pipelines/pipeline_mikudance.py:647-653)
+    refunet = None
+    if rank == 0 and world == 1 and not args.skip_reference_unet and not args.ncu_step:
+        try:
+            refunet = time_reference_unet(cfg, dev, h, min(F_, ctx_frames), len(loop.windows), num_steps, ms_step)
+        except Exception as e:  # noqa: BLE001 — never lose the bench line to the optional extra
+            refunet = dict(error=f"{type(e).__name__}: {e}")
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         t, fps, cores, note = cpu_reference_sample(h, num_steps, 1, 0, budget_s=15.0)
@@ -413,7 +458,7 @@ def main():
                     roofline_step=dict(bound="tensor", algorithmic_tflop_per_step=step_tflop,
                                        achieved=step_ach, peak=peaks["tflops_sustained"], unit="TFLOP/s",
                                        frac=(step_ach / peaks["tflops_sustained"]) if step_ach else None),
-                    kernels=kernels, top_shapes=shapes, cpu_baseline=cpu)
+                    reference_unet=refunet, kernels=kernels, top_shapes=shapes, cpu_baseline=cpu)
         print(json.dumps(line))
     if world > 1:
         # drop the captured graph (it holds NCCL work) before tearing the communicator down, and never

@@ -661,12 +661,43 @@ def check_refunet_tiny():
 
 
 def check_refunet_a():
-    """SD-1.5 sized reference UNet at BASELINE config A's latent size (32x32), 4 frames x 2 branches."""
+    """SD-1.5 sized reference UNet at BASELINE config A's latent size (32x32), one frame x 2 branches."""
     from mikudance_b200 import synth
-    return refunet_check(synth.SD15_CONFIG, 8, 32, 32, 257, "cfgA")[0]
+    return refunet_check(synth.SD15_CONFIG, 2, 32, 32, 257, "cfgA")[0]
+
+
+def perf_refunet():
+    """Reference UNet at BASELINE config B's shape: 32 images (16 frames x 2 CFG branches) of 96x96 latents,
+    SD-1.5 size, 257 CLIP tokens — the once-per-window cost of the hoisted writer."""
+    from mikudance_b200 import _lib, synth
+    cfg = synth.SD15_CONFIG
+    m, _ = build_refunet(cfg)
+    N, h = 32, 96
+    x, ctx = synth.synthetic_reference_inputs(cfg, N, h, h, lctx=257)
+    x, ctx = x.to(DEV, F16), ctx.to(DEV, F16)
+    eng = m.engine()
+    eng.set_timestep(0)
+    n0 = _lib.launch_count()
+    eng.run(x, ctx)
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - n0
+    ms = timeit(lambda: eng.run(x, ctx), iters=3, warm=1)
+    prof = ops.Profiler()
+    ops.set_profiler(prof)
+    eng.run(x, ctx)
+    torch.cuda.synchronize()
+    ops.set_profiler(None)
+    summ = prof.summary()
+    fl = sum(v["flops"] for v in summ.values())
+    print(f"perf refunet N={N} {h}x{h}: {ms:.2f} ms per forward, {launches} launches, "
+          f"{fl / 1e12:.2f} TFLOP launched -> {fl / (ms * 1e-3) / 1e12:.0f} TFLOP/s")
+    for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"]):
+        print(f"perf refunet   {k:14s} n={v['n']:4d} {v['ms']:8.3f} ms  {v.get('tflops', 0):7.1f} TFLOP/s  {v.get('gbs', 0):7.0f} GB/s")
+    return True
 
 
 CHECKS = {
+    "perf_refunet": perf_refunet,
     "refunet_ops": check_refunet_ops, "refunet_tiny": check_refunet_tiny, "refunet_a": check_refunet_a,
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
