@@ -8,8 +8,11 @@ Everything step-dependent (timestep, DDIM coefficients) is read from device memo
 captured graph is replayed for every step; per step the host only writes 1 + 4 scalars.
 
 Frame sharding: rank r of G runs the UNet on frames [r*fl, (r+1)*fl) of every window (both CFG
-branches); the motion modules all-gather K/V over NCCL (engine._motion); the window accumulators are
-summed across ranks once per step (2.4 MB at 768x768x16f) and the DDIM update is replicated.
+branches); the motion modules exchange frames<->pixels (or all-gather K/V) over NCCL (engine._motion);
+the window accumulators are summed across ranks once per step (2.4 MB at 768x768x16f) and the DDIM
+update is replicated.  With MDK_CFG_SPLIT=1 (even G, guidance on; off by default until it has run on
+NCCL) the two CFG branches go to the two halves of the ranks instead (sharding.plan_ranks): the
+motion-module exchange then spans G/2 ranks — none at G = 2.
 """
 from __future__ import annotations
 
@@ -19,7 +22,7 @@ import torch
 
 from . import ops
 from .context import get_context_scheduler
-from .sharding import shard_window, slice_bank
+from .sharding import plan_ranks, shard_window, slice_bank
 
 F16 = torch.float16
 
@@ -44,7 +47,18 @@ class DenoiseLoop:
             self.rank = dist.get_rank(process_group)
         else:
             self.world, self.rank = 1, 0
-        self.eng.set_process_group(process_group, self.rank, self.world)
+        import os
+        plan = plan_ranks(self.rank, self.world, self.do_cfg, os.environ.get("MDK_CFG_SPLIT", "0") == "1")
+        self.branch, self.sub_rank, self.sub_world = plan["branch"], plan["sub_rank"], plan["sub_world"]
+        if self.branch >= 0:
+            import torch.distributed as dist
+            ranks = dist.get_process_group_ranks(process_group)
+            half = self.sub_world
+            # every rank creates both branch groups (new_group is collective), then keeps its own
+            groups = [dist.new_group(ranks[b * half:(b + 1) * half]) for b in (0, 1)] if half > 1 else [None, None]
+            self.eng.set_process_group(groups[self.branch], self.sub_rank, half)
+        else:
+            self.eng.set_process_group(process_group, self.rank, self.world)
         self.use_graph = use_cuda_graph
         self.graph = None
 
@@ -56,7 +70,8 @@ class DenoiseLoop:
         banks_for_window(window) -> {attention path: [(nb * len(window)) , hw, C]} full-window banks
         (the stand-in for / output of the reference UNet; this rank slices its frames)."""
         dev = self.dev
-        assert latents.is_cuda and latents.dtype == F16 and latents.is_contiguous()
+        # the engine only exists on a CUDA device (UNetEngine refuses CPU models): same device required
+        assert latents.device == dev and latents.dtype == F16 and latents.is_contiguous()
         self.latents = latents
         _, self.c, self.F, self.h, self.w = latents.shape
         self.nb = 2 if self.do_cfg else 1
@@ -69,15 +84,18 @@ class DenoiseLoop:
         self.win = []
         for wdw in self.windows:
             L = len(wdw)
-            mine, lo = shard_window(wdw, self.rank, self.world)
+            mine, lo = shard_window(wdw, self.sub_rank, self.sub_world)
             fl = len(mine)
             idx = torch.tensor(mine, dtype=torch.int32, device=dev)
             banks = None
             if banks_for_window is not None:
                 full = banks_for_window(wdw)
-                if full is not None:
-                    banks = {k: slice_bank(v, self.nb, L, self.rank, self.world)
-                             .to(device=dev, dtype=F16).contiguous() for k, v in full.items()}
+                if full is not None and self.branch != 0:          # the uncond branch never reads a bank
+                    banks = {k: slice_bank(v, self.nb, L, self.sub_rank, self.sub_world)
+                             .to(device=dev, dtype=F16) for k, v in full.items()}
+                    if self.branch == 1:                           # cond branch only: second half of (b fl)
+                        banks = {k: v[fl:] for k, v in banks.items()}
+                    banks = {k: v.contiguous() for k, v in banks.items()}
             self.win.append(dict(frames=wdw, idx=idx, fl=fl, f_off=lo, L=L, banks=banks))
         self.acc = torch.zeros((self.nb, self.c, self.F, self.h, self.w), dtype=torch.float32, device=dev)
         self.counter = torch.zeros(self.F, dtype=torch.float32, device=dev)
@@ -97,13 +115,23 @@ class DenoiseLoop:
         self.acc.zero_()
         self.counter.zero_()
         n_unc_all = self.do_cfg
+        br = self.branch
         for wd in self.win:
             fl = wd["fl"]
-            x_in = ops.latents_to_nhwc(self.latents, b=self.nb, frame_idx=wd["idx"], fl=fl,
-                                       cpad=eng.cin_pad)
-            pred = eng.run(x_in, self.nb, fl, self.h, self.w, self.ctx, wd["banks"],
-                           n_uncond=(fl if n_unc_all else 0), f_off=wd["f_off"], f_total=wd["L"])
-            ops.pred_accumulate(pred, self.acc, self.counter, frame_idx=wd["idx"], fl=fl)
+            if br < 0:
+                x_in = ops.latents_to_nhwc(self.latents, b=self.nb, frame_idx=wd["idx"], fl=fl,
+                                           cpad=eng.cin_pad)
+                pred = eng.run(x_in, self.nb, fl, self.h, self.w, self.ctx, wd["banks"],
+                               n_uncond=(fl if n_unc_all else 0), f_off=wd["f_off"], f_total=wd["L"])
+                ops.pred_accumulate(pred, self.acc, self.counter, frame_idx=wd["idx"], fl=fl)
+            else:
+                # CFG split: this rank evaluates ONE branch; its row of the accumulator gets the prediction,
+                # the other row stays zero until the all-reduce; the uncond ranks own the frame counter
+                x_in = ops.latents_to_nhwc(self.latents, b=1, frame_idx=wd["idx"], fl=fl, cpad=eng.cin_pad)
+                pred = eng.run(x_in, 1, fl, self.h, self.w, self.ctx[br:br + 1], wd["banks"],
+                               n_uncond=(fl if br == 0 else 0), f_off=wd["f_off"], f_total=wd["L"])
+                ops.pred_accumulate(pred, self.acc[br:br + 1], self.counter if br == 0 else None,
+                                    frame_idx=wd["idx"], fl=fl)
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.acc, group=self.pg)

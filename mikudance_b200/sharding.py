@@ -17,6 +17,21 @@ from typing import Dict, List, Sequence, Tuple
 import torch
 
 
+def plan_ranks(rank: int, world: int, do_cfg: bool, cfg_split: bool) -> Dict[str, int]:
+    """Which images rank `rank` of `world` evaluates.
+    Frame sharding (default): every rank runs both CFG branches of its frames: branch = -1 (both),
+    sub_rank = rank, sub_world = world.
+    CFG split (`cfg_split`, needs guidance and an even world): the two CFG branches never interact inside
+    the UNet (they only meet in the guidance formula, pipeline_mikudance.py:670-674), so ranks
+    [0, world/2) take the uncond branch and [world/2, world) the cond branch; frames are sharded over the
+    world/2 ranks of a branch and the motion-module exchange stays inside that half-size group (none at
+    all at world == 2)."""
+    if cfg_split and do_cfg and world >= 2 and world % 2 == 0:
+        half = world // 2
+        return dict(branch=rank // half, sub_rank=rank % half, sub_world=half)
+    return dict(branch=-1, sub_rank=rank, sub_world=world)
+
+
 def shard_window(window: Sequence[int], rank: int, world: int) -> Tuple[List[int], int]:
     """(frames of `window` owned by `rank`, offset of the first one inside the window)."""
     L = len(window)

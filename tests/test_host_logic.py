@@ -105,3 +105,37 @@ def test_geglu_panel_packing():
     assert bp[:128].tolist() == list(range(0, 128)) and bp[128:256].tolist() == list(range(512, 640))
     assert bp[256:384].tolist() == list(range(128, 256))
     assert torch.equal(wp[:, 0].float(), bp * 2)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """ABI drift guard: size and every field offset of the ctypes mirrors in mikudance_b200/_lib.py equal
+    what a C compiler computes from include/mdk.h."""
+    import shutil
+    import subprocess
+    from mikudance_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = [("mdk_gemm_args", _lib.GemmArgs), ("mdk_attn_args", _lib.AttnArgs), ("mdk_tattn_args", _lib.TattnArgs),
+             ("mdk_gn_args", _lib.GnArgs), ("mdk_ln_args", _lib.LnArgs), ("mdk_temb_args", _lib.TembArgs),
+             ("mdk_man_args", _lib.ManArgs)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mdk.h"', 'int main(void){']
+    for cname, st in pairs:
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append('return 0;}')
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "mdk.h")).read(), flags=re.S)
+    for cname, st in pairs:
+        assert int(got[cname]) == ctypes.sizeof(st), cname
+        for fname, _ in st._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(st, fname).offset, f"{cname}.{fname}"
+        # and no field of the C struct is missing from the mirror
+        body = [seg for seg in hdr.split("typedef struct {") if re.search(r"\}\s*" + cname + r"\s*;", seg)][0]
+        body = body[:body.index("}")]
+        c_fields = re.findall(r"([a-z_0-9]+)(?:\[\d+\])?\s*[;,]", body)
+        assert set(c_fields) == {f for f, _ in st._fields_}, cname
