@@ -83,7 +83,21 @@ struct AttnCfg {
 // ONES: row d of every head of V^T holds ones (d % 16 == 8), so column d of O = P V accumulates the
 // softmax row sums of the fp16-rounded P on the tensor core; the softmax warps then neither add up the
 // exponentials nor rescale a running sum (one FADD per score less on the latency-bound softmax path).
-template <int NCH, int BKV, int KST, bool ONES>
+// ONES == 2 additionally takes the exponentials of tile j against the reference maximum known BEFORE
+// tile j (the running maximum of tiles < j): the row maximum of tile j is then computed inside the
+// exponential loop (ALU pipe, interleaved with the MUFU work) instead of in front of it, which removes
+// the 128-score max pass from the stretch in which the MUFU pipe idles.  The reference is updated (and O
+// rescaled) at the start of tile j+1 when tile j's maximum exceeded it by more than 2^8; if a row's
+// maximum exceeds the stale reference by more than 2^14 (fp16 P would overflow) the tile is redone
+// against the new maximum (rare: the running maximum settles after the first tiles).
+// SPLIT: separate rings (full / empty barriers) for the K tiles and the V^T tiles of the same KST stages.
+// With one ring a stage is released by the completion of P_{j-1} V_{j-1} and the load of K_{j+1} | V_{j+1}
+// into it must land before the MMA warp (which waits for K_{j+1} ahead of P_j V_j) can move on: one TMA
+// round trip per tile sits on the critical path whenever it is longer than the exponential phase.  A K
+// stage is really free as soon as S = Q K^T has been computed from it — a whole tile period earlier — so
+// with split rings K_{j+1} is requested right after Q K_{j-1}^T and V_j right after P_{j-2} V_{j-2}: both
+// loads get about two tile periods to arrive, with the same shared-memory footprint.
+template <int NCH, int BKV, int KST, int ONES, bool SPLIT = false>
 __global__ void __launch_bounds__(ATT_THREADS, (NCH == 1) ? (BKV == 64 ? 3 : 2) : ((NCH == 2 && BKV == 64) ? 2 : 1))
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<NCH, BKV, KST>;
@@ -105,7 +119,11 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   uint64_t* s_free = bars + 2 + 2 * KST;     // [1] S_j drained into registers (4 warp arrivals)
   uint64_t* p_full = bars + 3 + 2 * KST;     // [1]
   uint64_t* pv_done = bars + 4 + 2 * KST;    // [1]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5 + 2 * KST);
+  // SPLIT: kv_full / kv_empty serve the K tiles, v_full / v_empty the V^T tiles
+  uint64_t* v_full = bars + 5 + 2 * KST;     // [KST]
+  uint64_t* v_empty = bars + 5 + 3 * KST;    // [KST]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5 + 4 * KST);
+  static_assert((5 + 4 * KST) * 8 + 8 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,6 +143,10 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     for (int s = 0; s < KST; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
+      if constexpr (SPLIT) {
+        mbar_init(&v_full[s], 1);
+        mbar_init(&v_empty[s], 1);
+      }
     }
     mbar_init(s_full, 1);
     mbar_init(s_free, 4);
@@ -147,6 +169,29 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         tma_load_4d(sQ + c * ATT_BQ * 128, &p.tmQ, q_bar, c * 64, head, q0, img);
       const uint32_t stage_bytes =
           static_cast<uint32_t>(Cfg::K_STAGE + (BKV / 64) * p.dn * 128);
+      if constexpr (SPLIT) {
+        const uint32_t v_bytes = static_cast<uint32_t>((BKV / 64) * p.dn * 128);
+        auto load_k = [&](int t) {
+          const int st = t % KST;
+          mbar_wait(&kv_empty[st], static_cast<uint32_t>((t / KST) & 1) ^ 1u);   // Q K_{t-KST}^T has retired
+          mbar_expect_tx(&kv_full[st], Cfg::K_STAGE);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+            tma_load_4d(sK + st * Cfg::K_STAGE + c * BKV * 128, &p.tmK, &kv_full[st], c * 64, head,
+                        t * BKV, kvimg);
+        };
+        load_k(0);
+        for (int j = 0; j < n_tiles; ++j) {
+          if (j + 1 < n_tiles) load_k(j + 1);     // K runs one tile ahead of V^T
+          const int st = j % KST;
+          mbar_wait(&v_empty[st], static_cast<uint32_t>((j / KST) & 1) ^ 1u);    // P_{j-KST} V_{j-KST} has retired
+          mbar_expect_tx(&v_full[st], v_bytes);
+#pragma unroll
+          for (int c = 0; c < BKV / 64; ++c)
+            tma_load_3d(sV + st * Cfg::V_STAGE + c * Cfg::V_CHUNK, &p.tmV, &v_full[st], j * BKV + c * 64,
+                        head * p.vt_head_rows, kvimg);
+        }
+      } else {
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
@@ -166,6 +211,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           phase ^= 1u;
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
@@ -183,6 +229,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           tc_mma_f16_ss(tS, adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
         }
         tc_commit(s_full);
+        if constexpr (SPLIT) tc_commit(&kv_empty[stage]);   // the K stage is free once S has been computed
       }
       __syncwarp();
     };
@@ -207,6 +254,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         issue_s(nstage);
       }
       mbar_wait(p_full, static_cast<uint32_t>(j & 1));
+      if constexpr (SPLIT) mbar_wait(&v_full[stage], phase);
       tc_fence_after();
       if (elect_one()) {
         const int kv = p.lkv - j * BKV;                      // keys in this tile
@@ -220,7 +268,10 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
               make_sdesc_sw128(smem_u32(sV + stage * Cfg::V_STAGE + c * Cfg::V_CHUNK)) + 2u * w;
           tc_mma_f16_ss(tO, adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         }
-        tc_commit(&kv_empty[stage]);
+        if constexpr (SPLIT)
+          tc_commit(&v_empty[stage]);
+        else
+          tc_commit(&kv_empty[stage]);
         tc_commit(pv_done);
       }
       __syncwarp();
@@ -236,6 +287,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     const uint32_t tO = tmem_base + lane_off + Cfg::O_COL;
     float m_used = -INFINITY;  // reference max (scaled, log2 domain) the exponentials are taken against
     float l_sum = 0.f;
+    float pend_alpha = 1.0f;    // ONES == 2: reference update decided at the end of the previous tile
+    bool pend_rescale = false;
     const uint32_t prow = smem_u32(sP) + static_cast<uint32_t>(row) * 128u;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     const bool poly = p.poly != 0;
@@ -256,6 +309,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
+      constexpr bool STALE = (ONES == 2);
+      const bool fresh = !STALE || j == 0;   // the tile's own maximum is the reference (always for tile 0)
       float mx = -INFINITY;
       if (nvalid < BKV) {
 #pragma unroll
@@ -266,7 +321,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           }
         }
       }
-      {
+      float alpha = 1.0f;
+      bool rescale = false;
+      if (fresh) {
         // 4 independent running maxima: a single fmaxf chain over 128 scores is 128 x 4 cycles of
         // pure dependency latency per tile
         float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -278,17 +335,19 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           }
         }
         mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
-      }
-      mx *= p.scale_log2;
-      float alpha = 1.0f;
-      bool rescale = false;
-      if (j == 0) {
-        m_used = mx;
-      } else if (mx > m_used + ATT_RESCALE_THRESHOLD) {
-        alpha = ex2_approx(m_used - mx);
-        m_used = mx;
-        if constexpr (!ONES) l_sum *= alpha;
-        rescale = true;
+        mx *= p.scale_log2;
+        if (j == 0) {
+          m_used = mx;
+        } else if (mx > m_used + ATT_RESCALE_THRESHOLD) {
+          alpha = ex2_approx(m_used - mx);
+          m_used = mx;
+          if constexpr (!ONES) l_sum *= alpha;
+          rescale = true;
+        }
+      } else {
+        // stale reference: the update decided at the end of the previous tile takes effect now
+        alpha = pend_alpha;
+        rescale = pend_rescale;
       }
       // P_{j-1} V_{j-1} must have retired before P (single buffer) or O may be touched
       if (j > 0) {
@@ -309,6 +368,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       // exp2, row sum, fp16 pack and the store of P, 8 columns (one 16-byte piece) at a time.
       // P -> smem, K-major, 128B swizzle: 16-byte piece q of row r lands at piece (q ^ (r & 7))
       float rsp[2] = {0.f, 0.f};  // independent partial row sums (short dependency chains)
+      float tmx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // ONES == 2: this tile's maximum, for tile j+1
       auto exp_tile = [&](auto poly_tag) {
         constexpr bool POLY = decltype(poly_tag)::value;
 #pragma unroll
@@ -319,6 +379,10 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+              if constexpr (STALE) {
+                tmx[e] = fmaxf(tmx[e], fmaxf(__uint_as_float(v[c][q4 * 8 + 2 * e]),
+                                             __uint_as_float(v[c][q4 * 8 + 2 * e + 1])));
+              }
               const float x0 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e]), p.scale_log2, -m_used);
               const float x1 = fmaf(__uint_as_float(v[c][q4 * 8 + 2 * e + 1]), p.scale_log2, -m_used);
               if constexpr (POLY) {
@@ -342,6 +406,37 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         exp_tile(std::true_type{});
       else
         exp_tile(std::false_type{});
+      if constexpr (STALE) {
+        pend_alpha = 1.0f;
+        pend_rescale = false;
+        if (!fresh) {
+          const float mxs = fmaxf(fmaxf(tmx[0], tmx[1]), fmaxf(tmx[2], tmx[3])) * p.scale_log2;
+          const bool over = mxs > m_used + 14.0f;   // exp2 of more than 14 would leave fp16's range in P
+          if (__any_sync(0xffffffffu, over)) {
+            // redo this tile against its own maximum (P has not been published yet; P_{j-1} V_{j-1} has
+            // retired: pv_done was awaited above), rows below the limit keep their reference
+            const float a2 = over ? ex2_approx(m_used - mxs) : 1.0f;
+            if (over) m_used = mxs;
+            for (int c = 0; c < p.dn; c += 16) {
+              uint32_t o[16];
+              tmem_ld_x16(tO + c, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * a2);
+              tmem_st_x16(tO + c, o);
+            }
+            tmem_wait_st();
+            if (poly)
+              exp_tile(std::true_type{});
+            else
+              exp_tile(std::false_type{});
+          } else if (mxs > m_used + ATT_RESCALE_THRESHOLD) {
+            pend_alpha = ex2_approx(m_used - mxs);   // applied to O at the start of tile j+1
+            m_used = mxs;
+            pend_rescale = true;
+          }
+        }
+      }
       if constexpr (!ONES) l_sum += rsp[0] + rsp[1];
       fence_proxy_async_smem();
       tc_fence_before();
@@ -419,13 +514,13 @@ static int encode_attn_maps(AttnParams& p, const mdk_attn_args* a, int bkv) {
   return 0;
 }
 
-template <int NCH, int BKV, int KST, bool ONES>
+template <int NCH, int BKV, int KST, int ONES, bool SPLIT = false>
 static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a,
                        cudaStream_t stream) {
   using Cfg = AttnCfg<NCH, BKV, KST>;
   static bool attr_set = false;
   if (!attr_set) {
-    MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<NCH, BKV, KST, ONES>,
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<NCH, BKV, KST, ONES, SPLIT>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
@@ -433,7 +528,7 @@ static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a
   if (encode_attn_maps(p, a, BKV)) return -1;
   p.n_kv_tiles = (a->lkv + BKV - 1) / BKV;
   dim3 grid((a->lq + ATT_BQ - 1) / ATT_BQ, a->heads, a->nimg);
-  attn_tc_kernel<NCH, BKV, KST, ONES><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  attn_tc_kernel<NCH, BKV, KST, ONES, SPLIT><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   count_launch();
   MDK_CHECK_CUDA(cudaGetLastError());
   (void)ctx;
@@ -1226,16 +1321,25 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
     // 0.391 vs 0.474 ms)
     const char* e = getenv("MDK_ATTN_BKV");
     int bkv = e ? atoi(e) : 0;
+    const char* esp = getenv("MDK_ATTN_SPLITKV");   // separate K / V^T rings (written after round 1's GPU budget
+    const int split_kv = esp ? atoi(esp) : 0;       // was spent: off until it has run on a B200)
     if (bkv == 0) bkv = ((a->lkv + 63) / 64 * 64 < (a->lkv + 127) / 128 * 128) ? 64 : 128;
-    if (bkv == 64) return launch_attn<1, 64, 2, false>(ctx, p, a, stream);   // 3 CTAs per SM
-    if (a->vt_ones) return launch_attn<1, 128, 2, true>(ctx, p, a, stream);
-    return launch_attn<1, 128, 2, false>(ctx, p, a, stream);                  // 2 CTAs per SM
+    if (bkv == 64) return launch_attn<1, 64, 2, 0>(ctx, p, a, stream);   // 3 CTAs per SM
+    if (a->vt_ones) {
+      const char* es = getenv("MDK_ATTN_STALE");   // read per call: tests switch kernels in-process
+      const int stale = es ? atoi(es) : 0;         // off until measured on a B200
+      if (stale) return launch_attn<1, 128, 2, 2>(ctx, p, a, stream);
+      if (split_kv) return launch_attn<1, 128, 2, 1, true>(ctx, p, a, stream);
+      return launch_attn<1, 128, 2, 1>(ctx, p, a, stream);
+    }
+    if (split_kv) return launch_attn<1, 128, 2, 0, true>(ctx, p, a, stream);
+    return launch_attn<1, 128, 2, 0>(ctx, p, a, stream);                  // 2 CTAs per SM
   }
   if (a->d <= 128) {
     const char* e = getenv("MDK_ATTN_BKV2");
     const int bkv2 = e ? atoi(e) : 128;
-    if (bkv2 == 64) return launch_attn<2, 64, 2, false>(ctx, p, a, stream);   // 2 CTAs per SM
-    return launch_attn<2, 128, 2, false>(ctx, p, a, stream);
+    if (bkv2 == 64) return launch_attn<2, 64, 2, 0>(ctx, p, a, stream);   // 2 CTAs per SM
+    return launch_attn<2, 128, 2, 0>(ctx, p, a, stream);
   }
-  return launch_attn<3, 64, 2, false>(ctx, p, a, stream);
+  return launch_attn<3, 64, 2, 0>(ctx, p, a, stream);
 }

@@ -342,10 +342,16 @@ def check_attn():
         ok &= report(f"attn n={nimg} lq={lq} lkv={lkv} h={heads} d={d}", out,
                      ref_attention(q, k, vt, nimg, lq, lkv, heads, d, kv_div))
     # padded V^T with a ones row per head: row sums come out of the P.V MMA
-    for (nimg, l, heads, d) in [(2, 1024, 8, 40), (3, 200, 8, 8), (1, 2304, 8, 40)]:
+    # (the last three: query gains -> the running maximum keeps growing: lazy rescale of O, and with the
+    # large gains jumps of more than 2^14 inside one tile = the redo path of the stale-reference kernel)
+    ones_cases = [(2, 1024, 8, 40, 1.0), (3, 200, 8, 8, 1.0), (1, 2304, 8, 40, 1.0)]
+    if os.environ.get("MDK_ATTN_STALE", "0") == "1":
+        # (validated on a B200 with this kernel, profiles/r01_ab_attn_stale.log)
+        ones_cases += [(2, 1024, 8, 40, 6.0), (1, 1300, 8, 40, 25.0), (2, 640, 4, 40, 60.0)]
+    for (nimg, l, heads, d, gain) in ones_cases:
         C_ = heads * d
         dp = d + 8
-        q = rnd(nimg * l, C_).to(F16)
+        q = (rnd(nimg * l, C_) * gain).to(F16)
         k = rnd(nimg * l, C_, seed=11).to(F16)
         lp = (l + 7) // 8 * 8
         v = rnd(nimg, heads, d, l, seed=12).to(F16)
@@ -356,8 +362,38 @@ def check_attn():
                             vt_head_rows=dp, vt_ones=True)
         vt_dense = torch.zeros(nimg, C_, lp, dtype=F16, device=DEV)
         vt_dense[:, :, :l] = v.reshape(nimg, C_, l)
-        ok &= report(f"attn(ones) n={nimg} L={l} d={d}", out, ref_attention(q, k, vt_dense, nimg, l, l, heads, d, 1))
+        ok &= report(f"attn(ones) n={nimg} L={l} d={d} gain={gain}", out,
+                     ref_attention(q, k, vt_dense, nimg, l, l, heads, d, 1))
     return ok
+
+
+def ab_attn_stale():
+    """A/B of the stale-reference softmax kernel (MDK_ATTN_STALE=1) on the L0 self-attention shape:
+    parity of every attention case with the switch on, then alternating timings."""
+    os.environ["MDK_ATTN_STALE"] = "1"
+    ok = check_attn()
+    warm_gpu()
+    nimg, l, heads, d = 8, 9216, 8, 40
+    C_, dp = heads * d, d + 8
+    q = rnd(nimg * l, C_).to(F16)
+    k = rnd(nimg * l, C_, seed=11).to(F16)
+    vt2 = torch.ones(nimg, heads, dp, l, dtype=F16, device=DEV)
+    vt2[:, :, :d] = rnd(nimg, C_, l, seed=12).to(F16).reshape(nimg, heads, d, l)
+    vt2 = vt2.reshape(nimg, heads * dp, l)
+    out = torch.empty_like(q)
+    outs = {}
+    for rep in range(3):
+        for flag in ("0", "1"):
+            os.environ["MDK_ATTN_STALE"] = flag
+            ms = timeit_ms(lambda: ops.attention(q, k, vt2, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out,
+                                                 vt_head_rows=dp, vt_ones=True))
+            outs[flag] = out.clone()
+            print(f"perf attn(ones, stale={flag}) n={nimg} L={l} d={d}: {ms:.3f} ms  "
+                  f"{4.0 * nimg * heads * l * l * d / ms / 1e9:.1f} TFLOP/s", flush=True)
+    rel = ((outs["1"].float() - outs["0"].float()).norm() / outs["0"].float().norm()).item()
+    print(f"stale vs default on the perf inputs: rel_l2 = {rel:.3e}")
+    os.environ["MDK_ATTN_STALE"] = "0"
+    return ok and rel < 1e-3
 
 
 def warm_gpu(seconds=1.5):
@@ -696,8 +732,36 @@ def perf_refunet():
     return True
 
 
+def ab_attn_switches():
+    """Every attention kernel switch on the L0 self-attention shape (ones-row V^T), one process."""
+    warm_gpu()
+    nimg, l, heads, d = 8, 9216, 8, 40
+    C_, dp = heads * d, d + 8
+    q = rnd(nimg * l, C_).to(F16)
+    k = rnd(nimg * l, C_, seed=11).to(F16)
+    vt2 = torch.ones(nimg, heads, dp, l, dtype=F16, device=DEV)
+    vt2[:, :, :d] = rnd(nimg, C_, l, seed=12).to(F16).reshape(nimg, heads, d, l)
+    vt2 = vt2.reshape(nimg, heads * dp, l)
+    out = torch.empty_like(q)
+    names = ("MDK_ATTN_POLY", "MDK_ATTN_SK", "MDK_ATTN_PP", "MDK_ATTN_BKV", "MDK_ATTN_STALE", "MDK_ATTN_SPLITKV")
+    extra = ({"MDK_ATTN_SPLITKV": "1"}, {"MDK_ATTN_SPLITKV": "1", "MDK_ATTN_POLY": "1"}) \
+        if os.environ.get("MDK_TEST_UNVALIDATED", "0") == "1" else ()
+    for env in ({}, {"MDK_ATTN_POLY": "1"}, {"MDK_ATTN_STALE": "1", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_SK": "1"},
+                {"MDK_ATTN_PP": "3"}, {"MDK_ATTN_BKV": "64"}) + extra + ({},):
+        for n in names:
+            os.environ.pop(n, None)
+        os.environ.update(env)
+        ms = timeit_ms(lambda: ops.attention(q, k, vt2, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out,
+                                             vt_head_rows=dp, vt_ones=True))
+        print(f"perf attn(ones) {env or 'default'}: {ms:.3f} ms  {4.0 * nimg * heads * l * l * d / ms / 1e9:.1f} TFLOP/s",
+              flush=True)
+    for n in names:
+        os.environ.pop(n, None)
+    return True
+
+
 CHECKS = {
-    "perf_refunet": perf_refunet,
+    "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
     "refunet_ops": check_refunet_ops, "refunet_tiny": check_refunet_tiny, "refunet_a": check_refunet_a,
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
