@@ -64,7 +64,7 @@ def pixels_per_rank(hw: int, world: int) -> int:
 def frames_to_pixels(x: torch.Tensor, nb: int, fl: int, hw: int, world: int, group) -> torch.Tensor:
     """x [(nb fl) hw, C], this rank's fl frames of every pixel  ->  [(nb F) pp, C] with F = world*fl:
     ALL frames (window order: source rank major) of this rank's pp = ceil(hw / world) pixels.
-    Pixels >= hw (only when hw % world != 0) are zero rows."""
+    Pixels >= hw (only when hw % world != 0) are zero rows.  ONE all-to-all for both CFG branches."""
     import torch.distributed as dist
     C = x.shape[-1]
     pp = pixels_per_rank(hw, world)
@@ -72,11 +72,10 @@ def frames_to_pixels(x: torch.Tensor, nb: int, fl: int, hw: int, world: int, gro
     if pp * world != hw:
         pad = torch.zeros((nb, fl, pp * world - hw, C), dtype=x.dtype, device=x.device)
         xv = torch.cat([xv, pad], dim=2)
-    send = xv.view(nb, fl, world, pp, C).permute(0, 2, 1, 3, 4).contiguous()   # [nb, G(dst), fl, pp, C]
-    recv = torch.empty_like(send)                                              # [nb, G(src), fl, pp, C]
-    for b in range(nb):
-        dist.all_to_all_single(recv[b], send[b], group=group)
-    return recv.view(nb * world * fl * pp, C)
+    send = xv.view(nb, fl, world, pp, C).permute(2, 0, 1, 3, 4).contiguous()   # [G(dst), nb, fl, pp, C]
+    recv = torch.empty_like(send)                                              # [G(src), nb, fl, pp, C]
+    dist.all_to_all_single(recv, send, group=group)
+    return recv.permute(1, 0, 2, 3, 4).reshape(nb * world * fl * pp, C)        # [nb, G(src), fl, pp, C]
 
 
 def pixels_to_frames(h: torch.Tensor, nb: int, fl: int, hw: int, world: int, group) -> torch.Tensor:
@@ -84,11 +83,10 @@ def pixels_to_frames(h: torch.Tensor, nb: int, fl: int, hw: int, world: int, gro
     import torch.distributed as dist
     C = h.shape[-1]
     pp = pixels_per_rank(hw, world)
-    hv = h.view(nb, world, fl, pp, C)                                          # [nb, G(dst frames), fl, pp, C]
-    back = torch.empty_like(hv)                                                # [nb, G(pixel chunk), fl, pp, C]
-    for b in range(nb):
-        dist.all_to_all_single(back[b], hv[b], group=group)
-    out = back.permute(0, 2, 1, 3, 4).reshape(nb, fl, world * pp, C)
+    send = h.view(nb, world, fl, pp, C).permute(1, 0, 2, 3, 4).contiguous()    # [G(dst frames), nb, fl, pp, C]
+    back = torch.empty_like(send)                                              # [G(pixel chunk), nb, fl, pp, C]
+    dist.all_to_all_single(back, send, group=group)
+    out = back.permute(1, 2, 0, 3, 4).reshape(nb, fl, world * pp, C)
     if pp * world != hw:
         out = out[:, :, :hw]
     return out.reshape(nb * fl * hw, C)
