@@ -6,7 +6,14 @@ SRC := $(wildcard mikudance_b200/csrc/*.cu)
 OBJ := $(patsubst mikudance_b200/csrc/%.cu,build/%.o,$(SRC))
 LIB := mikudance_b200/lib/libmikudance_sm100.so
 
-all: $(LIB)
+MICRO := build/softmax_loop_bench
+
+all: $(LIB) $(MICRO)
+
+# diagnostic microbenchmark (not product): the attention softmax loop's instruction mix in isolation
+build/softmax_loop_bench: tests/micro/softmax_loop_bench.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -o $@ $<
 
 build/%.o: mikudance_b200/csrc/%.cu mikudance_b200/csrc/ptx.cuh mikudance_b200/csrc/host_common.h include/mdk.h
 	@mkdir -p build
