@@ -88,3 +88,35 @@ def test_refunet_engine_orchestration_matches_oracle(monkeypatch):
         assert blk.bank[0].shape == (N, (h // ds) * (w // ds), c)
     writer.clear()
     assert all(len(b.bank) == 0 for b in writer._blocks(model))
+
+
+def test_forward_argument_errors(monkeypatch):
+    """Error behaviour of the forward call surfaces (raised before any kernel is launched)."""
+    from mikudance_b200 import synth
+    from mikudance_b200.engine import UNetEngine
+    from mikudance_b200.engine_ref import RefUNetEngine
+    from mikudance_b200.unet_2d_ref import UNet2DConditionModel
+    K.install(monkeypatch)
+    cfg = synth.TINY_CONFIG
+    m = _unet3d(cfg).half().eval()
+    eng = K.engine_on_cpu(UNetEngine, m)
+    ctx = torch.zeros(1, 3, cfg["cross_attention_dim"], dtype=torch.float16)
+    with pytest.raises(ValueError, match="divisible by 8"):
+        eng.forward_api(torch.zeros(1, 4, 2, 12, 8, dtype=torch.float16), 1, ctx)
+    with pytest.raises(ValueError, match="temporal_position_encoding_max_len"):
+        eng.forward_api(torch.zeros(1, 4, 33, 8, 8, dtype=torch.float16), 1, ctx)        # window > PE table
+    with pytest.raises(ValueError, match="batch"):
+        eng.forward_api(torch.zeros(3, 4, 2, 8, 8, dtype=torch.float16), 1, ctx.repeat(2, 1, 1))
+    with pytest.raises(NotImplementedError, match="per-sample timesteps"):
+        eng.forward_api(torch.zeros(2, 4, 2, 8, 8, dtype=torch.float16), torch.tensor([1, 2]), ctx)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 4, 2, 8, 8), 1, ctx, class_labels=torch.zeros(1))
+    r = UNet2DConditionModel(block_out_channels=cfg["block_out_channels"],
+                             cross_attention_dim=cfg["cross_attention_dim"]).half().eval()
+    reng = K.engine_on_cpu(RefUNetEngine, r)
+    with pytest.raises(ValueError, match="22|input"):
+        reng.forward_api(torch.zeros(1, 4, 16, 16, dtype=torch.float16), 0, ctx)
+    with pytest.raises(ValueError, match="more than 1 spatial element"):
+        reng.forward_api(torch.zeros(1, 22, 8, 8, dtype=torch.float16), 0, ctx)          # nn.InstanceNorm2d raises too
+    with pytest.raises(ValueError, match="divisible by 8"):
+        reng.forward_api(torch.zeros(1, 22, 20, 16, dtype=torch.float16), 0, ctx)
