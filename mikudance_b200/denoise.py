@@ -71,7 +71,9 @@ class DenoiseLoop:
         (the stand-in for / output of the reference UNet; this rank slices its frames)."""
         dev = self.dev
         # the engine only exists on a CUDA device (UNetEngine refuses CPU models): same device required
-        assert latents.device == dev and latents.dtype == F16 and latents.is_contiguous()
+        same_dev = latents.device.type == dev.type and (
+            latents.device.index is None or dev.index is None or latents.device.index == dev.index)
+        assert same_dev and latents.dtype == F16 and latents.is_contiguous(), (latents.device, dev, latents.dtype)
         self.latents = latents
         _, self.c, self.F, self.h, self.w = latents.shape
         self.nb = 2 if self.do_cfg else 1
