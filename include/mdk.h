@@ -123,6 +123,12 @@ typedef struct {
 
 int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* args, void* stream);
 
+/* Diagnostics (never on the product path): with MDK_ATTN_TRACE=1 in the environment, launches of the
+ * ones-row 128-key attention kernel run an instrumented instantiation in which one CTA writes clock64()
+ * at the hand-off points of every key tile into buf[tile*16 + slot] (device memory, int64, `tiles` tiles;
+ * slots are listed in csrc/attn_tc.cu).  buf = NULL switches it off. */
+int mdk_attn_debug_trace(void* buf, int32_t tiles);
+
 /* ------------------------------------------------------------------------------------------
  * mdk_temporal_attn_f16 — attention across the frame axis at a fixed pixel (AnimateDiff motion
  * module). Replaces VersatileAttention.forward, src/models/motion_module.py:364-439 (the

@@ -58,6 +58,8 @@ struct AttnParams {
   float scale_log2;
   int vt_head_rows;  // rows per head in V^T (>= d)
   int poly;          // 1: every second pair of exponentials on the FMA pipe (ex2_poly_h2)
+  long long* trace;  // TRACE instantiation only: clock64 timeline of one CTA, [tile][16 slots]
+  int trace_cap;     // tiles the trace buffer holds
 };
 
 template <int NCH, int BKV, int KST>
@@ -97,7 +99,12 @@ struct AttnCfg {
 // stage is really free as soon as S = Q K^T has been computed from it — a whole tile period earlier — so
 // with split rings K_{j+1} is requested right after Q K_{j-1}^T and V_j right after P_{j-2} V_{j-2}: both
 // loads get about two tile periods to arrive, with the same shared-memory footprint.
-template <int NCH, int BKV, int KST, int ONES, bool SPLIT = false>
+// TRACE (diagnostic instantiation, MDK_ATTN_TRACE=1 + mdk_attn_debug_trace): the CTA in the middle of the
+// grid's x range (head 0, image 0) records clock64() at the hand-off points of every tile:
+//   softmax warp 2, lane 0:  0 S_j full   1 S_j in registers   2 P_{j-1}V_{j-1} done   3 exponentials done   4 P_j published
+//   MMA warp:                5 K_{j+1} landed   6 S_j drained   7 QK_{j+1}^T issued   8 P_j full (+ V_j landed)   9 P_j V_j issued
+//   TMA warp:               10 stage for tile j free   11 loads of tile j issued     (split rings: 10/11 = V^T, 12/13 = K)
+template <int NCH, int BKV, int KST, int ONES, bool SPLIT = false, bool TRACE = false>
 __global__ void __launch_bounds__(ATT_THREADS, (NCH == 1) ? (BKV == 64 ? 3 : 2) : ((NCH == 2 && BKV == 64) ? 2 : 1))
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<NCH, BKV, KST>;
@@ -132,6 +139,12 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   const int img = blockIdx.z;
   const int kvimg = img / p.kv_div;
   const int n_tiles = p.n_kv_tiles;
+  const bool tr_on = TRACE && p.trace != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+  auto tr = [&](int tile, int slot) {
+    if constexpr (TRACE) {
+      if (tr_on && tile < p.trace_cap) p.trace[tile * 16 + slot] = clock64();
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
@@ -174,28 +187,33 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         auto load_k = [&](int t) {
           const int st = t % KST;
           mbar_wait(&kv_empty[st], static_cast<uint32_t>((t / KST) & 1) ^ 1u);   // Q K_{t-KST}^T has retired
+          tr(t, 12);
           mbar_expect_tx(&kv_full[st], Cfg::K_STAGE);
 #pragma unroll
           for (int c = 0; c < NCH; ++c)
             tma_load_4d(sK + st * Cfg::K_STAGE + c * BKV * 128, &p.tmK, &kv_full[st], c * 64, head,
                         t * BKV, kvimg);
+          tr(t, 13);
         };
         load_k(0);
         for (int j = 0; j < n_tiles; ++j) {
           if (j + 1 < n_tiles) load_k(j + 1);     // K runs one tile ahead of V^T
           const int st = j % KST;
           mbar_wait(&v_empty[st], static_cast<uint32_t>((j / KST) & 1) ^ 1u);    // P_{j-KST} V_{j-KST} has retired
+          tr(j, 10);
           mbar_expect_tx(&v_full[st], v_bytes);
 #pragma unroll
           for (int c = 0; c < BKV / 64; ++c)
             tma_load_3d(sV + st * Cfg::V_STAGE + c * Cfg::V_CHUNK, &p.tmV, &v_full[st], j * BKV + c * 64,
                         head * p.vt_head_rows, kvimg);
+          tr(j, 11);
         }
       } else {
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1u);
+        tr(j, 10);
         mbar_expect_tx(&kv_full[stage], stage_bytes);
         const int kv0 = j * BKV;
 #pragma unroll
@@ -206,6 +224,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         for (int c = 0; c < BKV / 64; ++c)
           tma_load_3d(sV + stage * Cfg::V_STAGE + c * Cfg::V_CHUNK, &p.tmV, &kv_full[stage],
                       kv0 + c * 64, head * p.vt_head_rows, kvimg);
+        tr(j, 11);
         if (++stage == KST) {
           stage = 0;
           phase ^= 1u;
@@ -249,12 +268,16 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       }
       if (j + 1 < n_tiles) {
         mbar_wait(&kv_full[nstage], nphase);
+        if (lane == 0) tr(j, 5);
         mbar_wait(s_free, static_cast<uint32_t>(j & 1));
+        if (lane == 0) tr(j, 6);
         tc_fence_after();
         issue_s(nstage);
+        if (lane == 0) tr(j, 7);
       }
       mbar_wait(p_full, static_cast<uint32_t>(j & 1));
       if constexpr (SPLIT) mbar_wait(&v_full[stage], phase);
+      if (lane == 0) tr(j, 8);
       tc_fence_after();
       if (elect_one()) {
         const int kv = p.lkv - j * BKV;                      // keys in this tile
@@ -275,6 +298,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         tc_commit(pv_done);
       }
       __syncwarp();
+      if (lane == 0) tr(j, 9);
       stage = nstage;
       phase = nphase;
     }
@@ -293,8 +317,10 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     const bool poly = p.poly != 0;
 
+    const bool tr_sm = (warp == 2 && lane == 0);
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, static_cast<uint32_t>(j & 1));
+      if (tr_sm) tr(j, 0);
       tc_fence_after();
       // 32-column chunks of this tile that hold real keys (the last tile of a ragged sequence, e.g. the
       // 257 CLIP tokens, may need only one): the others are neither loaded, exponentiated nor fed to P V
@@ -305,6 +331,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       for (int c = 0; c < BKV / 32; ++c)
         if (c < nch) tmem_ld_x32(tS + c * 32, v[c]);
       tmem_wait_ld();
+      if (tr_sm) tr(j, 1);
       // S_j now lives in registers: the tensor core may overwrite it with S_{j+1}
       tc_fence_before();
       __syncwarp();
@@ -354,6 +381,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         mbar_wait(pv_done, static_cast<uint32_t>((j - 1) & 1));
         tc_fence_after();
       }
+      if (tr_sm) tr(j, 2);
       if (__any_sync(0xffffffffu, rescale)) {
         for (int c = 0; c < p.dn; c += 16) {
           uint32_t o[16];
@@ -438,10 +466,12 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         }
       }
       if constexpr (!ONES) l_sum += rsp[0] + rsp[1];
+      if (tr_sm) tr(j, 3);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (tr_sm) tr(j, 4);
     }
     // ---- epilogue: O / l ----
     mbar_wait(pv_done, static_cast<uint32_t>((n_tiles - 1) & 1));
@@ -514,13 +544,18 @@ static int encode_attn_maps(AttnParams& p, const mdk_attn_args* a, int bkv) {
   return 0;
 }
 
-template <int NCH, int BKV, int KST, int ONES, bool SPLIT = false>
+static long long* g_attn_trace = nullptr;   // set by mdk_attn_debug_trace (diagnostics only)
+static int g_attn_trace_cap = 0;
+
+template <int NCH, int BKV, int KST, int ONES, bool SPLIT = false, bool TRACE = false>
 static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a,
                        cudaStream_t stream) {
   using Cfg = AttnCfg<NCH, BKV, KST>;
   static bool attr_set = false;
+  p.trace = TRACE ? g_attn_trace : nullptr;
+  p.trace_cap = TRACE ? g_attn_trace_cap : 0;
   if (!attr_set) {
-    MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<NCH, BKV, KST, ONES, SPLIT>,
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<NCH, BKV, KST, ONES, SPLIT, TRACE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
@@ -528,7 +563,7 @@ static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a
   if (encode_attn_maps(p, a, BKV)) return -1;
   p.n_kv_tiles = (a->lkv + BKV - 1) / BKV;
   dim3 grid((a->lq + ATT_BQ - 1) / ATT_BQ, a->heads, a->nimg);
-  attn_tc_kernel<NCH, BKV, KST, ONES, SPLIT><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  attn_tc_kernel<NCH, BKV, KST, ONES, SPLIT, TRACE><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   count_launch();
   MDK_CHECK_CUDA(cudaGetLastError());
   (void)ctx;
@@ -1259,6 +1294,12 @@ int mdk_attn_set_wait_ns(unsigned ns) {
 
 }  // namespace mdk
 
+extern "C" int mdk_attn_debug_trace(void* buf, int32_t tiles) {
+  mdk::g_attn_trace = static_cast<long long*>(buf);
+  mdk::g_attn_trace_cap = buf ? tiles : 0;
+  return 0;
+}
+
 extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stream_) {
   using namespace mdk;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -1329,6 +1370,11 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
       const char* es = getenv("MDK_ATTN_STALE");   // read per call: tests switch kernels in-process
       const int stale = es ? atoi(es) : 0;         // off until measured on a B200
       if (stale) return launch_attn<1, 128, 2, 2>(ctx, p, a, stream);
+      const char* etr = getenv("MDK_ATTN_TRACE");
+      if (etr && atoi(etr) && g_attn_trace != nullptr) {   // timeline of one CTA (tests/gpu_diag.py trace_attn)
+        if (split_kv) return launch_attn<1, 128, 2, 1, true, true>(ctx, p, a, stream);
+        return launch_attn<1, 128, 2, 1, false, true>(ctx, p, a, stream);
+      }
       if (split_kv) return launch_attn<1, 128, 2, 1, true>(ctx, p, a, stream);
       return launch_attn<1, 128, 2, 1>(ctx, p, a, stream);
     }

@@ -12,6 +12,8 @@ echo "== 1. parity of the kernels written without a GPU (split K / V^T rings)" |
 ( MDK_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_kernels_gpu.py -q -x -k "split_kv" 2>&1 | tail -6 ) | tee -a $L
 echo "== 2. every attention switch on the L0 self-attention shape (incl. MDK_ATTN_SPLITKV)" | tee -a $L
 ( MDK_TEST_UNVALIDATED=1 timeout 60 python tests/gpu_diag.py ab_attn_switches 2>&1 | grep -E "^perf|PASS|FAIL|EXC" ) | tee -a $L
+echo "== 2b. per-tile timeline of one CTA (which wait sets the period)" | tee -a $L
+( MDK_TEST_UNVALIDATED=1 timeout 60 python tests/gpu_diag.py trace_attn 2>&1 | grep -E "trace|softmax warp|MMA warp|TMA warp|PASS|FAIL|EXC" ) | tee -a $L
 echo "== 3. softmax inner-loop ceiling (pure instruction mix)" | tee -a $L
 ( timeout 15 ./build/softmax_loop_bench 2>&1 | tail -16 ) | tee -a $L
 echo "== 4. step time with / without the split rings (only meaningful if 1. passed)" | tee -a $L

@@ -760,8 +760,56 @@ def ab_attn_switches():
     return True
 
 
+def trace_attn():
+    """Software timeline of ONE CTA of the L0 self-attention kernel (MDK_ATTN_TRACE=1 instantiation): median
+    SM cycles between the hand-off points of a key tile, for the default ring and (MDK_TEST_UNVALIDATED=1) the
+    split K / V^T rings.  Answers which wait sets the tile period (PERF.md, next experiments 1)."""
+    from mikudance_b200 import _lib
+    lib = _lib.load_library()
+    warm_gpu(0.5)
+    nimg, l, heads, d = 8, 9216, 8, 40
+    C_, dp = heads * d, d + 8
+    q = rnd(nimg * l, C_).to(F16)
+    k = rnd(nimg * l, C_, seed=11).to(F16)
+    vt2 = torch.ones(nimg, heads, dp, l, dtype=F16, device=DEV)
+    vt2[:, :, :d] = rnd(nimg, C_, l, seed=12).to(F16).reshape(nimg, heads, d, l)
+    vt2 = vt2.reshape(nimg, heads * dp, l)
+    out = torch.empty_like(q)
+    ntile = l // 128
+    variants = [("default ring", {})]
+    if os.environ.get("MDK_TEST_UNVALIDATED", "0") == "1":
+        variants.append(("split K/V rings", {"MDK_ATTN_SPLITKV": "1"}))
+    for name, env in variants:
+        buf = torch.zeros(ntile * 16, dtype=torch.int64, device=DEV)
+        lib.mdk_attn_debug_trace(buf.data_ptr(), ntile)
+        os.environ["MDK_ATTN_TRACE"] = "1"
+        os.environ.update(env)
+        for _ in range(2):
+            ops.attention(q, k, vt2, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out, vt_head_rows=dp, vt_ones=True)
+        torch.cuda.synchronize()
+        os.environ.pop("MDK_ATTN_TRACE", None)
+        for kk in env:
+            os.environ.pop(kk, None)
+        lib.mdk_attn_debug_trace(None, 0)
+        t = buf.cpu().view(ntile, 16).double()
+        mid = slice(8, ntile - 4)       # steady state
+
+        def med(a, b, shift_b=0):       # median of slot a (tile j) minus slot b (tile j - shift_b)
+            x = t[mid, a] - (t[mid, b] if shift_b == 0 else t[slice(8 - shift_b, ntile - 4 - shift_b), b])
+            x = x[(t[mid, a] > 0)]
+            return float(x.median()) if x.numel() else float("nan")
+        print(f"trace attn [{name}]: tile period {med(4, 4, 1):.0f} cycles")
+        print(f"  softmax warp: wait S_j {med(0, 4, 1):.0f} | TMEM load {med(1, 0):.0f} | max + wait PV_(j-1) {med(2, 1):.0f} | "
+              f"exponentials + P store {med(3, 2):.0f} | fence + publish {med(4, 3):.0f}")
+        print(f"  MMA warp    : wait K_(j+1) after PV_(j-1) issue {med(5, 9, 1):.0f} | wait S_j drained {med(6, 5):.0f} | issue QK {med(7, 6):.0f} | "
+              f"wait P_j {med(8, 7):.0f} | issue PV {med(9, 8):.0f}")
+        print(f"  TMA warp    : stage free -> loads issued {med(11, 10):.0f}; loads issued -> K_(j+1) seen by MMA warp "
+              f"{float((t[mid, 5] - t[slice(9, ntile - 3), 13 if env else 11]).median()):.0f}", flush=True)
+    return True
+
+
 CHECKS = {
-    "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
+    "trace_attn": trace_attn, "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
     "refunet_ops": check_refunet_ops, "refunet_tiny": check_refunet_tiny, "refunet_a": check_refunet_a,
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
