@@ -298,9 +298,13 @@ def main():
             return
         reps = max(1, args.steps)
         t, fps, cores, note = cpu_reference_sample(h, num_steps, reps, max(0, min(args.warmup, 1)), budget_s=90.0)
+        from mikudance_b200.context import get_context_scheduler
+        wins = [len(w) for w in get_context_scheduler("uniform")(0, num_steps, F_, ctx_frames, 1, 8)]
         line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
                     warmup=args.warmup, ms_per_step=t * F_ * 1e3, higher_is_better=True, scaling="strong",
-                    vs_baseline=None, dtype="f32", data="synthetic", impl="reference", config=workload,
+                    vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                    config=dict(workload, parallelism=f"host cores ({cores} threads), no GPU", windows=wins,
+                                l2="n/a (CPU)", cuda_graph=False),
                     cpu_baseline=dict(value=fps, unit="frames/s", cores=cores, kind="port",
                                       sample=f"1 of {F_} frames (2 CFG images) of one UNet forward per timed "
                                              f"step ({note}), fp32 oracle of the reference modules; clip "
