@@ -298,6 +298,14 @@ typedef struct {
 int64_t mdk_man_ws_bytes(int32_t nimg, int32_t c);
 int mdk_man_modulate_f16(mdk_ctx* ctx, const mdk_man_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * CLIP image encoder (transformers CLIPVisionModelWithProjection as used at
+ * src/pipelines/pipeline_mikudance.py:405-417).  It runs on mdk_gemm_f16 (patch embedding as a GEMM whose
+ * row bias is the position embedding; q|k|v, out, fc1, fc2, visual_projection), mdk_layernorm_f16 and
+ * mdk_attn_fwd_f16; the only op of its own is the MLP activation:
+ * mdk_quick_gelu_f16 — in place x * sigmoid(1.702 x) over n fp16 values (n % 8 == 0). */
+int mdk_quick_gelu_f16(mdk_ctx* ctx, void* x, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,4 +1,5 @@
-// Kernels that only the reference UNet (writer) needs — SURVEY.md §8f row 1:
+// Kernels of the stages around the denoising loop.  CLIP image encoder: the in-place
+// QuickGELU of its MLP.  Reference UNet (writer):
 //   * condition-latent layout change: channel slice of an NCHW batch -> zero-padded NHWC, with the
 //     nearest-neighbour resize MANModule applies to the scene-motion map,
 //   * in-place ReLU (MANModule.mlp_shared),
@@ -30,6 +31,23 @@ __global__ void cond_to_nhwc_kernel(const __half* __restrict__ x, __half* __rest
     __half* dst = out + i * cpad;
     for (int ch = 0; ch < cpad; ++ch)
       dst[ch] = ch < c ? src[static_cast<long long>(ch) * h * w] : __float2half(0.f);
+  }
+}
+
+// CLIP's MLP activation, in place: x * sigmoid(1.702 x)  (transformers QuickGELUActivation), fp32 math
+__global__ void quick_gelu_kernel(uint4* __restrict__ x, long long nvec) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint4 v = x[i];
+    __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __half22float2(h[e]);
+      f.x = __fdividef(f.x, 1.0f + __expf(-1.702f * f.x));
+      f.y = __fdividef(f.y, 1.0f + __expf(-1.702f * f.y));
+      h[e] = __floats2half2_rn(f.x, f.y);
+    }
+    x[i] = v;
   }
 }
 
@@ -197,6 +215,23 @@ extern "C" int mdk_relu_f16(mdk_ctx* ctx, void* x, int64_t n, void* stream_) {
   const long long cap = static_cast<long long>(ctx->num_sms) * 8;
   if (blocks > cap) blocks = cap;
   relu_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<uint4*>(x), nvec);
+  count_launch();
+  MDK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mdk_quick_gelu_f16(mdk_ctx* ctx, void* x, int64_t n, void* stream_) {
+  using namespace mdk;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MDK_REQUIRE(ctx && x, "mdk_quick_gelu_f16: null argument");
+  MDK_REQUIRE(n % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+              "mdk_quick_gelu_f16: n must be a multiple of 8 and x 16-byte aligned");
+  if (n <= 0) return 0;
+  const long long nvec = n / 8;
+  long long blocks = (nvec + 255) / 256;
+  const long long cap = static_cast<long long>(ctx->num_sms) * 8;
+  if (blocks > cap) blocks = cap;
+  quick_gelu_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<uint4*>(x), nvec);
   count_launch();
   MDK_CHECK_CUDA(cudaGetLastError());
   return 0;

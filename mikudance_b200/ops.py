@@ -387,3 +387,15 @@ def man_modulate(x: torch.Tensor, gb: torch.Tensor, *, nimg: int, hw: int, eps: 
          lambda: load_library().mdk_man_modulate_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
          "mdk_man_modulate_f16")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP image encoder only — SURVEY.md §8f row 3
+# ------------------------------------------------------------------------------------------------
+def quick_gelu_(x: torch.Tensor) -> torch.Tensor:
+    _chk16(x, "x")
+    assert x.is_contiguous()
+    _run("quick_gelu", 0.0, 4.0 * x.numel(),
+         lambda: load_library().mdk_quick_gelu_f16(get_ctx(x.device), ptr(x), x.numel(), cur_stream(x.device)),
+         "mdk_quick_gelu_f16")
+    return x

@@ -251,3 +251,58 @@ def synthetic_reference_inputs(cfg, n_img: int, h: int, w: int, lctx: int = 257,
     pair = torch.cat([torch.zeros_like(c), c], dim=0)
     ctx = pair.repeat((n_img + 1) // 2, 1, 1)[:n_img]
     return x, ctx
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP image encoder (transformers.CLIPVisionModelWithProjection key set) — SURVEY.md §8f row 3
+# ------------------------------------------------------------------------------------------------
+CLIP_VITL14_CONFIG = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                          image_size=224, patch_size=14, projection_dim=768, layer_norm_eps=1e-5)
+CLIP_TINY_CONFIG = dict(hidden_size=128, intermediate_size=512, num_hidden_layers=3, num_attention_heads=2,
+                        image_size=56, patch_size=14, projection_dim=64, layer_norm_eps=1e-5)
+
+
+def clip_state_dict_spec(cfg) -> List[Tuple[str, Tuple[int, ...], str]]:
+    C, I, P = cfg["hidden_size"], cfg["intermediate_size"], cfg["patch_size"]
+    ntok = (cfg["image_size"] // P) ** 2 + 1
+    v = "vision_model."
+    spec: List[Tuple[str, Tuple[int, ...], str]] = [
+        (v + "embeddings.class_embedding", (C,), "e"),
+        (v + "embeddings.patch_embedding.weight", (C, 3, P, P), "w"),
+        (v + "embeddings.position_embedding.weight", (ntok, C), "e"),
+        (v + "pre_layrnorm.weight", (C,), "g"), (v + "pre_layrnorm.bias", (C,), "b"),
+    ]
+    for i in range(cfg["num_hidden_layers"]):
+        l = f"{v}encoder.layers.{i}."
+        for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            spec += [(l + f"self_attn.{n}.weight", (C, C), "w"), (l + f"self_attn.{n}.bias", (C,), "b")]
+        spec += [(l + "layer_norm1.weight", (C,), "g"), (l + "layer_norm1.bias", (C,), "b"),
+                 (l + "mlp.fc1.weight", (I, C), "w"), (l + "mlp.fc1.bias", (I,), "b"),
+                 (l + "mlp.fc2.weight", (C, I), "w"), (l + "mlp.fc2.bias", (C,), "b"),
+                 (l + "layer_norm2.weight", (C,), "g"), (l + "layer_norm2.bias", (C,), "b")]
+    spec += [(v + "post_layernorm.weight", (C,), "g"), (v + "post_layernorm.bias", (C,), "b"),
+             ("visual_projection.weight", (cfg["projection_dim"], C), "w")]
+    return spec
+
+
+def synthetic_clip_state_dict(cfg, seed: int = 0, dtype=torch.float16) -> Dict[str, torch.Tensor]:
+    sd = {}
+    for name, shape, kind in clip_state_dict_spec(cfg):
+        if kind == "w":
+            fan_in = 1
+            for s_ in shape[1:]:
+                fan_in *= s_
+            t = _seeded_randn(name, shape, seed) / math.sqrt(fan_in)
+        elif kind == "g":
+            t = 1.0 + 0.1 * _seeded_randn(name, shape, seed)
+        elif kind == "b":
+            t = 0.02 * _seeded_randn(name, shape, seed)
+        else:
+            t = 0.1 * _seeded_randn(name, shape, seed)
+        sd[name] = t.to(dtype)
+    return sd
+
+
+def synthetic_pixel_values(cfg, n: int, seed: int = 400) -> torch.Tensor:
+    """CLIPImageProcessor-like input: [n, 3, image_size, image_size], roughly unit scale."""
+    return _seeded_randn("clip_pixels", (n, 3, cfg["image_size"], cfg["image_size"]), seed)

@@ -13,6 +13,9 @@ What comes from where:
                            sample, four of the sixteen feature banks in full and the L2 norm / mean of all
                            sixteen (in the writer/reader pairing order); refunet_state_dict_sd15.json is
                            its key -> shape contract at the SD-1.5 size.
+  * clip_tiny.npz        — outputs of transformers.CLIPVisionModelWithProjection (installed in this image) on
+                           synthetic weights: last_hidden_state and the pipelines' image_prompt_embeds;
+                           clip_state_dict_vitl14.json is its key -> shape contract at ViT-L/14 size.
   * context_windows.json — outputs of the reference's src/pipelines/context.py (imports untouched).
   * state_dict_sd15.json — key -> shape of the reference model built with the SD-1.5 config +
                            configs/inference/mikudance_config.yaml (the weight-container contract).
@@ -128,6 +131,25 @@ def main():
     json.dump(rshapes, open(os.path.join(OUT, "refunet_state_dict_sd15.json"), "w"), indent=0)
     print("reference-unet sd15 tensors", len(rshapes), "params", sum(int(np.prod(s)) for s in rshapes.values()))
     del bigref
+
+    # CLIP image embedding (third-party transformers, installed here): outputs of the real model
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    ccfg = synth.CLIP_TINY_CONFIG
+    clip = CLIPVisionModelWithProjection(CLIPVisionConfig(**ccfg)).eval()
+    csd = {k: v.float() for k, v in synth.synthetic_clip_state_dict(ccfg, seed=0).items()}
+    missing = clip.load_state_dict(csd, strict=False)
+    assert not missing.unexpected_keys and all("position_ids" in k for k in missing.missing_keys), missing
+    px = synth.synthetic_pixel_values(ccfg, 2).half().float()
+    with torch.no_grad():
+        o = clip(px)
+        emb = clip.visual_projection(clip.vision_model.post_layernorm(o.last_hidden_state))   # pipeline :405-417
+    np.savez_compressed(os.path.join(OUT, "clip_tiny.npz"), last_hidden_state=o.last_hidden_state.numpy(),
+                        image_prompt_embeds=emb.numpy())
+    big = CLIPVisionModelWithProjection(CLIPVisionConfig(**synth.CLIP_VITL14_CONFIG))
+    json.dump({k: list(v.shape) for k, v in big.state_dict().items() if "position_ids" not in k},
+              open(os.path.join(OUT, "clip_state_dict_vitl14.json"), "w"), indent=0)
+    print("clip_tiny", tuple(emb.shape), float(emb.abs().mean()))
+    del big
 
     spec = importlib.util.spec_from_file_location("refctx", os.path.join(REF, "src/pipelines/context.py"))
     refctx = importlib.util.module_from_spec(spec)

@@ -702,6 +702,41 @@ def check_refunet_a():
     return refunet_check(synth.SD15_CONFIG, 2, 32, 32, 257, "cfgA")[0]
 
 
+def check_clip(cfg=None, n=2, tag="tiny"):
+    """native CLIP image encoder (last_hidden_state and the pipelines' image_prompt_embeds) vs the fp32 oracle."""
+    from mikudance_b200 import synth
+    from mikudance_b200.clip_vision import CLIPVisionModelWithProjection
+    from oracle import clip_oracle as Co
+    cfg = cfg or synth.CLIP_TINY_CONFIG
+    sd = synth.synthetic_clip_state_dict(cfg, seed=0)
+    m = CLIPVisionModelWithProjection(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(device=DEV, dtype=F16).eval()
+    px = synth.synthetic_pixel_values(cfg, n).half()
+    lh = m(px.to(DEV)).last_hidden_state
+    emb = m.visual_projection(m.vision_model.post_layernorm(lh))           # the pipelines' three calls
+    emb2 = m.image_prompt_embeds(px.to(DEV))
+    torch.cuda.synchronize()
+    sd32 = {k: v.float() for k, v in sd.items()}
+    with torch.no_grad():
+        lho = Co.clip_last_hidden_state(sd32, cfg, px.float())
+        embo = Co.image_prompt_embeds(sd32, cfg, px.float())
+    ok = report(f"clip {tag} last_hidden_state", lh.cpu().reshape(-1, lh.shape[-1]), lho.reshape(-1, lho.shape[-1]), tol=5e-3)
+    ok &= report(f"clip {tag} image_prompt_embeds", emb.cpu().reshape(-1, emb.shape[-1]), embo.reshape(-1, embo.shape[-1]), tol=5e-3)
+    ok &= bool(torch.equal(emb, emb2))
+    a = rnd(1000, 128, seed=3).to(F16)
+    ref = a.float() * torch.sigmoid(1.702 * a.float())
+    ops.quick_gelu_(a)
+    torch.cuda.synchronize()
+    ok &= report("quick_gelu", a, ref, tol=1e-3)
+    return ok
+
+
+def check_clip_vitl14():
+    from mikudance_b200 import synth
+    return check_clip(synth.CLIP_VITL14_CONFIG, 1, "ViT-L/14")
+
+
 def perf_refunet():
     """Reference UNet at BASELINE config B's shape: 32 images (16 frames x 2 CFG branches) of 96x96 latents,
     SD-1.5 size, 257 CLIP tokens — the once-per-window cost of the hoisted writer."""
@@ -809,7 +844,7 @@ def trace_attn():
 
 
 CHECKS = {
-    "trace_attn": trace_attn, "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
+    "clip": check_clip, "clip_vitl14": check_clip_vitl14, "trace_attn": trace_attn, "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
     "refunet_ops": check_refunet_ops, "refunet_tiny": check_refunet_tiny, "refunet_a": check_refunet_a,
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,

@@ -208,6 +208,12 @@ def cond_to_nhwc(x, *, c_first, c, ho, wo, cpad):
     return out
 
 
+def quick_gelu_(x):
+    xf = x.double()
+    x.copy_(_h(xf * torch.sigmoid(1.702 * xf)))
+    return x
+
+
 def relu_(x):
     x.copy_(torch.relu(x))
     return x
@@ -226,7 +232,7 @@ def man_modulate(x, gb, *, nimg, hw, eps=1e-5):
 
 _NAMES = ["gemm", "attention", "temporal_attention", "groupnorm", "layernorm", "upsample2x", "im2col3x3",
           "time_embed", "latents_to_nhwc", "cond_to_nhwc", "relu_", "man_modulate", "pred_accumulate",
-          "cfg_ddim_step"]
+          "cfg_ddim_step", "quick_gelu_"]
 
 
 def install(monkeypatch):
