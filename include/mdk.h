@@ -306,6 +306,21 @@ int mdk_man_modulate_f16(mdk_ctx* ctx, const mdk_man_args* args, void* stream);
  * mdk_quick_gelu_f16 — in place x * sigmoid(1.702 x) over n fp16 values (n % 8 == 0). */
 int mdk_quick_gelu_f16(mdk_ctx* ctx, void* x, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * VAE (diffusers AutoencoderKL as used at src/pipelines/pipeline_mikudance.py:115-130,
+ * 455-549).  Convolutions, GroupNorm+SiLU, the nearest upsample and the linears run on the entry points above;
+ * two ops are its own:
+ * mdk_softmax_rows_f16 — in-place softmax over the first `cols` columns of each of `rows` rows (row stride ld,
+ *   fp16 storage, fp32 math).  The mid-block attention has ONE head of 512 channels (beyond the flash kernel's
+ *   head size), so it runs as S = Q K^T (GEMM, the softmax scale folded into the q projection), this row softmax,
+ *   O = P V (GEMM against V^T).
+ * mdk_im2col3x3_ex_f16 — im2col of a 3x3 convolution with pad_lo (0 or 1) zero rows/columns in front and one
+ *   behind: Downsample2D(padding=0) of the encoder pads right/bottom only (F.pad(x, (0,1,0,1)), stride 2).
+ *   Output [nimg*ho*wo, kpad], ho = (h + pad_lo - 2)/stride + 1, column (kh*3+kw)*c + ci, zero padded. */
+int mdk_softmax_rows_f16(mdk_ctx* ctx, void* x, int64_t rows, int32_t cols, int64_t ld, void* stream);
+int mdk_im2col3x3_ex_f16(mdk_ctx* ctx, const void* x, void* out, int32_t nimg, int32_t h, int32_t w, int32_t c,
+                         int32_t stride, int32_t pad_lo, int32_t kpad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

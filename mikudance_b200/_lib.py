@@ -102,7 +102,7 @@ EXPORTS = [
     "mdk_im2col3x3_f16", "mdk_time_embed_f16", "mdk_latents_to_nhwc", "mdk_pred_accumulate",
     "mdk_cfg_ddim_step",
     "mdk_cond_to_nhwc_f16", "mdk_relu_f16", "mdk_man_ws_bytes", "mdk_man_modulate_f16",
-    "mdk_attn_debug_trace", "mdk_quick_gelu_f16",
+    "mdk_attn_debug_trace", "mdk_quick_gelu_f16", "mdk_softmax_rows_f16", "mdk_im2col3x3_ex_f16",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -147,6 +147,8 @@ def load_library() -> C.CDLL:
     lib.mdk_cond_to_nhwc_f16.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int32] * 9 + [c_void_p]
     lib.mdk_attn_debug_trace.argtypes = [c_void_p, c_int32]
     lib.mdk_quick_gelu_f16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    lib.mdk_softmax_rows_f16.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p]
+    lib.mdk_im2col3x3_ex_f16.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int32] * 7 + [c_void_p]
     lib.mdk_relu_f16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     lib.mdk_man_ws_bytes.restype = c_int64
     lib.mdk_man_ws_bytes.argtypes = [c_int32, c_int32]

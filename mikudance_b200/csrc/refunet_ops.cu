@@ -51,6 +51,87 @@ __global__ void quick_gelu_kernel(uint4* __restrict__ x, long long nvec) {
   }
 }
 
+// VAE mid-block attention (one head of 512 channels: beyond the flash kernel's head size, run as two GEMMs):
+// in-place row softmax of the fp16 score matrix, fp32 math, one CTA per row (three passes over a row that
+// stays in L1/L2: max, sum of exponentials, normalised write).
+__global__ void softmax_rows_kernel(__half* __restrict__ x, long long ld, int cols) {
+  __shared__ float s_red[32];
+  __half* row = x + static_cast<long long>(blockIdx.x) * ld;
+  const int nvec = cols >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  auto block_reduce = [&](float v, bool is_max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float t = __shfl_xor_sync(0xffffffffu, v, o);
+      v = is_max ? fmaxf(v, t) : v + t;
+    }
+    __syncthreads();           // s_red may still be read from the previous reduction
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    float r = s_red[0];
+    for (int w = 1; w < nwarp; ++w) r = is_max ? fmaxf(r, s_red[w]) : r + s_red[w];
+    return r;
+  };
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(row)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h[e]);
+      mx = fmaxf(mx, fmaxf(f.x, f.y));
+    }
+  }
+  mx = block_reduce(mx, true);
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(row)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h[e]);
+      sum += __expf(f.x - mx) + __expf(f.y - mx);
+    }
+  }
+  sum = block_reduce(sum, false);
+  const float inv = 1.0f / sum;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 v = reinterpret_cast<const uint4*>(row)[i];
+    __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h[e]);
+      h[e] = __floats2half2_rn(__expf(f.x - mx) * inv, __expf(f.y - mx) * inv);
+    }
+    reinterpret_cast<uint4*>(row)[i] = v;
+  }
+}
+
+// im2col of a 3x3 convolution with `pad_lo` zero rows / columns in front and one behind (the VAE encoder's
+// Downsample2D(padding=0) pads right / bottom only: pad_lo = 0, stride 2).  Same output layout as
+// im2col3x3_kernel (misc_ops.cu): [nimg*ho*wo, kpadv vectors], column (kh*3+kw)*c + ci.
+__global__ void im2col3x3_ex_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int nimg, int h, int w,
+                                    int cv, int stride, int pad_lo, int ho, int wo, int kpadv) {
+  const long long total = static_cast<long long>(nimg) * ho * wo * kpadv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kv = static_cast<int>(i % kpadv);
+    const long long m = i / kpadv;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (kv < 9 * cv) {
+      const int tap = kv / cv;
+      const int v = kv % cv;
+      const int ox = static_cast<int>(m % wo);
+      const int oy = static_cast<int>((m / wo) % ho);
+      const long long img = m / (static_cast<long long>(wo) * ho);
+      const int iy = oy * stride + tap / 3 - pad_lo;
+      const int ix = ox * stride + tap % 3 - pad_lo;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) val = x[((img * h + iy) * w + ix) * cv + v];
+    }
+    out[i] = val;
+  }
+}
+
 __global__ void relu_kernel(uint4* __restrict__ x, long long nvec) {
   const __half2 zero = __float2half2_rn(0.f);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
@@ -215,6 +296,40 @@ extern "C" int mdk_relu_f16(mdk_ctx* ctx, void* x, int64_t n, void* stream_) {
   const long long cap = static_cast<long long>(ctx->num_sms) * 8;
   if (blocks > cap) blocks = cap;
   relu_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<uint4*>(x), nvec);
+  count_launch();
+  MDK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mdk_softmax_rows_f16(mdk_ctx* ctx, void* x, int64_t rows, int32_t cols, int64_t ld, void* stream_) {
+  using namespace mdk;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MDK_REQUIRE(ctx && x, "mdk_softmax_rows_f16: null argument");
+  MDK_REQUIRE(cols > 0 && cols % 8 == 0 && ld % 8 == 0 && ld >= cols && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+              "mdk_softmax_rows_f16: cols=%d / ld=%lld must be multiples of 8, x 16-byte aligned", cols, (long long)ld);
+  MDK_REQUIRE(rows <= 2147483647LL, "mdk_softmax_rows_f16: too many rows");
+  if (rows <= 0) return 0;
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(static_cast<__half*>(x), ld, cols);
+  count_launch();
+  MDK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mdk_im2col3x3_ex_f16(mdk_ctx* ctx, const void* x, void* out, int32_t nimg, int32_t h, int32_t w,
+                                    int32_t c, int32_t stride, int32_t pad_lo, int32_t kpad, void* stream_) {
+  using namespace mdk;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MDK_REQUIRE(ctx && x && out, "mdk_im2col3x3_ex_f16: null argument");
+  MDK_REQUIRE(c % 8 == 0 && kpad % 8 == 0 && kpad >= 9 * c, "mdk_im2col3x3_ex_f16: c=%d kpad=%d", c, kpad);
+  MDK_REQUIRE(stride >= 1 && (pad_lo == 0 || pad_lo == 1) && h + pad_lo >= 2 && w + pad_lo >= 2,
+              "mdk_im2col3x3_ex_f16: bad stride / pad / size");
+  const int ho = (h + pad_lo - 2) / stride + 1, wo = (w + pad_lo - 2) / stride + 1;
+  const long long total = static_cast<long long>(nimg) * ho * wo * (kpad / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(ctx->num_sms) * 16;
+  if (blocks > cap) blocks = cap;
+  im2col3x3_ex_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(out), nimg, h, w, c / 8, stride, pad_lo, ho, wo, kpad / 8);
   count_launch();
   MDK_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -399,3 +399,28 @@ def quick_gelu_(x: torch.Tensor) -> torch.Tensor:
          lambda: load_library().mdk_quick_gelu_f16(get_ctx(x.device), ptr(x), x.numel(), cur_stream(x.device)),
          "mdk_quick_gelu_f16")
     return x
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE only — SURVEY.md §8f row 2
+# ------------------------------------------------------------------------------------------------
+def softmax_rows_(x: torch.Tensor) -> torch.Tensor:
+    """in-place softmax over the columns of x [rows, cols] fp16 (row stride x.stride(0))"""
+    _chk16(x, "x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    _run("softmax_rows", 0.0, 8.0 * rows * cols,
+         lambda: load_library().mdk_softmax_rows_f16(get_ctx(x.device), ptr(x), rows, cols, x.stride(0),
+                                                     cur_stream(x.device)), "mdk_softmax_rows_f16")
+    return x
+
+
+def im2col3x3_ex(x: torch.Tensor, nimg: int, h: int, w: int, stride: int, pad_lo: int) -> torch.Tensor:
+    _chk16(x, "x")
+    c = x.shape[1]
+    ho, wo = (h + pad_lo - 2) // stride + 1, (w + pad_lo - 2) // stride + 1
+    out = torch.empty((nimg * ho * wo, 9 * c), dtype=F16, device=x.device)
+    _run("im2col", 0.0, 2.0 * (nimg * h * w * c + out.numel()),
+         lambda: load_library().mdk_im2col3x3_ex_f16(get_ctx(x.device), ptr(x), ptr(out), nimg, h, w, c, stride,
+                                                     pad_lo, 9 * c, cur_stream(x.device)), "mdk_im2col3x3_ex_f16")
+    return out

@@ -306,3 +306,81 @@ def synthetic_clip_state_dict(cfg, seed: int = 0, dtype=torch.float16) -> Dict[s
 def synthetic_pixel_values(cfg, n: int, seed: int = 400) -> torch.Tensor:
     """CLIPImageProcessor-like input: [n, 3, image_size, image_size], roughly unit scale."""
     return _seeded_randn("clip_pixels", (n, 3, cfg["image_size"], cfg["image_size"]), seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE (diffusers.AutoencoderKL key set, SD-1.x geometry) — SURVEY.md §8f row 2
+# ------------------------------------------------------------------------------------------------
+SD_VAE_CONFIG = dict(in_channels=3, out_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512),
+                     layers_per_block=2, norm_num_groups=32, scaling_factor=0.18215)
+TINY_VAE_CONFIG = dict(SD_VAE_CONFIG, block_out_channels=(32, 64, 128, 128), norm_num_groups=8)
+
+
+def vae_state_dict_spec(cfg) -> List[Tuple[str, Tuple[int, ...], str]]:
+    boc, lpb, lat = list(cfg["block_out_channels"]), cfg["layers_per_block"], cfg["latent_channels"]
+    spec: List[Tuple[str, Tuple[int, ...], str]] = []
+
+    def norm(p, c):
+        spec.extend([(p + ".weight", (c,), "g"), (p + ".bias", (c,), "b")])
+
+    def conv(p, o, i, k):
+        spec.extend([(p + ".weight", (o, i, k, k), "w"), (p + ".bias", (o,), "b")])
+
+    def lin(p, o, i):
+        spec.extend([(p + ".weight", (o, i), "w"), (p + ".bias", (o,), "b")])
+
+    def resnet(p, ci, co):
+        norm(p + ".norm1", ci); conv(p + ".conv1", co, ci, 3); norm(p + ".norm2", co); conv(p + ".conv2", co, co, 3)
+        if ci != co:
+            conv(p + ".conv_shortcut", co, ci, 1)
+
+    def mid(p, c):
+        a = p + ".attentions.0"
+        norm(a + ".group_norm", c)
+        for n in ("to_q", "to_k", "to_v", "to_out.0"):
+            lin(f"{a}.{n}", c, c)
+        resnet(p + ".resnets.0", c, c)
+        resnet(p + ".resnets.1", c, c)
+
+    conv("encoder.conv_in", boc[0], cfg["in_channels"], 3)
+    ci = boc[0]
+    for i, co in enumerate(boc):
+        for j in range(lpb):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", ci if j == 0 else co, co)
+        if i < len(boc) - 1:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", co, co, 3)
+        ci = co
+    mid("encoder.mid_block", boc[-1])
+    norm("encoder.conv_norm_out", boc[-1])
+    conv("encoder.conv_out", 2 * lat, boc[-1], 3)
+    conv("quant_conv", 2 * lat, 2 * lat, 1)
+    conv("post_quant_conv", lat, lat, 1)
+    rev = list(reversed(boc))
+    conv("decoder.conv_in", rev[0], lat, 3)
+    mid("decoder.mid_block", rev[0])
+    ci = rev[0]
+    for i, co in enumerate(rev):
+        for j in range(lpb + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}", ci if j == 0 else co, co)
+        if i < len(rev) - 1:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", co, co, 3)
+        ci = co
+    norm("decoder.conv_norm_out", boc[0])
+    conv("decoder.conv_out", cfg["out_channels"], boc[0], 3)
+    return spec
+
+
+def synthetic_vae_state_dict(cfg, seed: int = 0, dtype=torch.float16) -> Dict[str, torch.Tensor]:
+    sd = {}
+    for name, shape, kind in vae_state_dict_spec(cfg):
+        if kind == "w":
+            fan_in = 1
+            for s_ in shape[1:]:
+                fan_in *= s_
+            t = _seeded_randn(name, shape, seed) / math.sqrt(fan_in)
+        elif kind == "g":
+            t = 1.0 + 0.1 * _seeded_randn(name, shape, seed)
+        else:
+            t = 0.02 * _seeded_randn(name, shape, seed)
+        sd[name] = t.to(dtype)
+    return sd

@@ -737,6 +737,53 @@ def check_clip_vitl14():
     return check_clip(synth.CLIP_VITL14_CONFIG, 1, "ViT-L/14")
 
 
+def check_vae(cfg=None, n=2, hw=(64, 96), tag="tiny"):
+    """native VAE encode (moments) / decode vs the fp32 restatement (oracle/vae_oracle.py; diffusers is absent:
+    parity unpinned), plus the two kernels of its own against plain PyTorch."""
+    from mikudance_b200 import synth
+    from mikudance_b200.vae import AutoencoderKL
+    from oracle import vae_oracle as Vo
+    import torch.nn.functional as Fn
+    cfg = cfg or synth.TINY_VAE_CONFIG
+    sd = synth.synthetic_vae_state_dict(cfg, seed=0)
+    m = AutoencoderKL(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(device=DEV, dtype=F16).eval()
+    sd32 = {k: v.float() for k, v in sd.items()}
+    H, W = hw
+    x = synth._seeded_randn("vae_img", (n, 3, H, W), 1).half()
+    mean = m.encode(x.to(DEV)).latent_dist.mean
+    z = (0.5 * synth._seeded_randn("vae_lat", (n, 4, H // 8, W // 8), 2)).half()
+    y = m.decode(z.to(DEV)).sample
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        mo = Vo.encode_mean(sd32, cfg, x.float())
+        yo = Vo.decode(sd32, cfg, z.float())
+    ok = report(f"vae {tag} encode mean", mean.cpu().reshape(-1, 1), mo.reshape(-1, 1), tol=5e-3)
+    ok &= report(f"vae {tag} decode", y.cpu().reshape(-1, 1), yo.reshape(-1, 1), tol=5e-3)
+    # own kernels
+    s_ = (rnd(300, 1024, seed=5) * 3).to(F16)
+    ref = torch.softmax(s_.float(), dim=-1)
+    ops.softmax_rows_(s_)
+    torch.cuda.synchronize()
+    ok &= report("softmax_rows", s_, ref, tol=1e-3)
+    a = rnd(2 * 12 * 20, 32, seed=6).to(F16)
+    col = ops.im2col3x3_ex(a, 2, 12, 20, 2, 0)
+    torch.cuda.synchronize()
+    xi = Fn.pad(a.float().view(2, 12, 20, 32).permute(0, 3, 1, 2), (0, 1, 0, 1))
+    cols = Fn.unfold(xi, 3, stride=2)
+    want = cols.view(2, 32, 9, -1).permute(0, 3, 2, 1).reshape(-1, 9 * 32)
+    e = bool(torch.equal(col.float(), want))
+    print(f"[{'OK ' if e else 'BAD'}] im2col3x3_ex pad_lo=0 stride 2 (exact)")
+    return ok and e
+
+
+def check_vae_sd():
+    """SD-1.x size VAE on one 256x256 image (1024 mid-block tokens)."""
+    from mikudance_b200 import synth
+    return check_vae(synth.SD_VAE_CONFIG, 1, (256, 256), "SD")
+
+
 def perf_refunet():
     """Reference UNet at BASELINE config B's shape: 32 images (16 frames x 2 CFG branches) of 96x96 latents,
     SD-1.5 size, 257 CLIP tokens — the once-per-window cost of the hoisted writer."""
@@ -844,7 +891,7 @@ def trace_attn():
 
 
 CHECKS = {
-    "clip": check_clip, "clip_vitl14": check_clip_vitl14, "trace_attn": trace_attn, "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
+    "vae": check_vae, "vae_sd": check_vae_sd, "clip": check_clip, "clip_vitl14": check_clip_vitl14, "trace_attn": trace_attn, "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
     "refunet_ops": check_refunet_ops, "refunet_tiny": check_refunet_tiny, "refunet_a": check_refunet_a,
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,

@@ -208,6 +208,20 @@ def cond_to_nhwc(x, *, c_first, c, ho, wo, cpad):
     return out
 
 
+def softmax_rows_(x):
+    x.copy_(_h(torch.softmax(x.double(), dim=-1)))
+    return x
+
+
+def im2col3x3_ex(x, nimg, h, w, stride, pad_lo):
+    c = x.shape[1]
+    xi = F.pad(x.double().view(nimg, h, w, c).permute(0, 3, 1, 2), (pad_lo, 1, pad_lo, 1))
+    cols = F.unfold(xi, 3, padding=0, stride=stride)
+    L = cols.shape[2]
+    assert L == ((h + pad_lo - 2) // stride + 1) * ((w + pad_lo - 2) // stride + 1)
+    return _h(cols.view(nimg, c, 9, L).permute(0, 3, 2, 1).reshape(nimg * L, 9 * c))
+
+
 def quick_gelu_(x):
     xf = x.double()
     x.copy_(_h(xf * torch.sigmoid(1.702 * xf)))
@@ -232,7 +246,7 @@ def man_modulate(x, gb, *, nimg, hw, eps=1e-5):
 
 _NAMES = ["gemm", "attention", "temporal_attention", "groupnorm", "layernorm", "upsample2x", "im2col3x3",
           "time_embed", "latents_to_nhwc", "cond_to_nhwc", "relu_", "man_modulate", "pred_accumulate",
-          "cfg_ddim_step", "quick_gelu_"]
+          "cfg_ddim_step", "quick_gelu_", "softmax_rows_", "im2col3x3_ex"]
 
 
 def install(monkeypatch):
