@@ -1369,6 +1369,7 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
     if (a->vt_ones) {
       const char* es = getenv("MDK_ATTN_STALE");   // read per call: tests switch kernels in-process
       const int stale = es ? atoi(es) : 0;         // off until measured on a B200
+      if (stale && split_kv) return launch_attn<1, 128, 2, 2, true>(ctx, p, a, stream);
       if (stale) return launch_attn<1, 128, 2, 2>(ctx, p, a, stream);
       const char* etr = getenv("MDK_ATTN_TRACE");
       if (etr && atoi(etr) && g_attn_trace != nullptr) {   // timeline of one CTA (tests/gpu_diag.py trace_attn)
