@@ -9,7 +9,7 @@ attention's K/V inside each motion module (torch.distributed plumbing, capturabl
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional
 
 import torch
 

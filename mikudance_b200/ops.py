@@ -9,7 +9,6 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-from . import _lib
 from ._lib import (AttnArgs, GemmArgs, GnArgs, LnArgs, ManArgs, TattnArgs, TembArgs, check, cur_stream,
                    get_ctx, load_library, ptr)
 

@@ -20,7 +20,7 @@ from typing import Union
 import torch
 from torch import nn
 
-from .synth import MAN_HIDDEN, REF_CHAR_CHANNELS, REF_MOTION_CHANNELS, block_plan
+from .synth import MAN_HIDDEN, REF_MOTION_CHANNELS, block_plan
 from .unet_3d import (Attention, FeedForward, TimestepEmbedding, _Conv1x1, _LayerNorm, _Linear,
                       _NoForward)
 

@@ -13,10 +13,9 @@ and launches CUDA kernels only.
 from __future__ import annotations
 
 import json
-import os
 from dataclasses import dataclass
 from types import SimpleNamespace
-from typing import Optional, Tuple, Union
+from typing import Union
 
 import torch
 from torch import nn
