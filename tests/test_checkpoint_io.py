@@ -113,3 +113,27 @@ def test_vae_and_clip_from_pretrained(tmp_path):
     hf = tr.CLIPVisionModelWithProjection(tr.CLIPVisionConfig(**ccfg))
     native = CLIPVisionModelWithProjection.from_transformers(hf)
     assert all(torch.equal(native.state_dict()[k], v) for k, v in hf.state_dict().items() if "position_ids" not in k)
+
+
+def test_video_io_round_trip(tmp_path):
+    """src.utils.util as imported by scripts/inference_video.py:24 (cv2-backed here; the reference uses PyAV)."""
+    from src.utils.util import get_fps, read_frames, save_videos_grid
+    vid = torch.zeros(2, 3, 5, 32, 48)
+    for t in range(5):
+        vid[0, :, t] = t / 4.0            # clip 0 brightens over time, clip 1 stays at 0.5
+    vid[1] = 0.5
+    path = str(tmp_path / "out" / "grid.mp4")
+    save_videos_grid(vid, path, n_rows=2, fps=12)
+    frames = read_frames(path)
+    assert len(frames) == 5 and frames[0].size == (2 * 48 + 3 * 2, 32 + 2 * 2)
+    assert float(get_fps(path)) == 12.0
+    import numpy as np
+    means = [np.asarray(f)[2:34, 2:50].mean() for f in frames]          # clip 0's cell
+    assert means == sorted(means) and means[0] < 10 and means[-1] > 245
+    assert abs(np.asarray(frames[2])[2:34, 52:100].mean() - 127.5) < 4   # clip 1's cell
+    save_videos_grid(vid[:1], str(tmp_path / "one.gif"), fps=8)
+    assert (tmp_path / "one.gif").stat().st_size > 0
+    with pytest.raises(ValueError):
+        save_videos_grid(vid, str(tmp_path / "x.avi"))
+    with pytest.raises(FileNotFoundError):
+        read_frames(str(tmp_path / "missing.mp4"))
