@@ -139,3 +139,34 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         body = body[:body.index("}")]
         c_fields = re.findall(r"([a-z_0-9]+)(?:\[\d+\])?\s*[;,]", body)
         assert set(c_fields) == {f for f, _ in st._fields_}, cname
+
+
+def test_inference_script_import_surface(monkeypatch):
+    """Every `src.*` name scripts/inference_video.py:17-24 imports resolves in this repository, and the opt-in
+    `compat/diffusers` stand-in provides the three diffusers names of line 10."""
+    import importlib
+    import sys
+    from src.models.unet_2d_condition import UNet2DConditionModel  # noqa: F401
+    from src.models.unet_2d_mix import UNet2DConditionModel as MIX  # noqa: F401
+    from src.models.unet_3d_mix import UNet3DConditionModel  # noqa: F401
+    from src.pipelines.pipeline_mikudance import MikuDanceVideoPipeline  # noqa: F401
+    from src.pipelines.pipeline_stage2_vdo import Pose2VideoPipeline  # noqa: F401
+    from src.utils.util import get_fps, read_frames, save_videos_grid  # noqa: F401
+    try:
+        import diffusers  # noqa: F401
+        pytest.skip("a real diffusers is installed: the stand-in must not be used")
+    except ImportError:
+        pass
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "compat"))
+    try:
+        d = importlib.import_module("diffusers")
+        assert d.AutoencoderKL.__module__ == "mikudance_b200.vae"
+        sch = d.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", clip_sample=False,
+                              steps_offset=1, prediction_type="v_prediction", rescale_betas_zero_snr=True,
+                              timestep_spacing="trailing")
+        sch.set_timesteps(20)
+        assert sch.timesteps.tolist()[:2] == [999, 949]
+        with pytest.raises(NotImplementedError):
+            d.AutoencoderKLTemporalDecoder.from_pretrained("x")
+    finally:
+        sys.modules.pop("diffusers", None)
