@@ -21,7 +21,9 @@ def _unet3d(cfg):
                                 unet_use_temporal_attention=False)
 
 
-@pytest.mark.parametrize("B,f,h,w,lctx,with_banks", [(2, 3, 16, 8, 9, True), (1, 2, 8, 8, 5, False)])
+@pytest.mark.parametrize("B,f,h,w,lctx,with_banks", [(2, 3, 16, 8, 9, True), (1, 2, 8, 8, 5, False),
+                                                      (1, 1, 8, 8, 3, True),        # a single frame
+                                                      (1, 32, 8, 8, 3, False)])     # the PE table's full length
 def test_unet3d_engine_orchestration_matches_oracle(monkeypatch, B, f, h, w, lctx, with_banks):
     from mikudance_b200 import synth
     from mikudance_b200.engine import UNetEngine
