@@ -1365,7 +1365,10 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
     const char* esp = getenv("MDK_ATTN_SPLITKV");   // separate K / V^T rings (written after round 1's GPU budget
     const int split_kv = esp ? atoi(esp) : 0;       // was spent: off until it has run on a B200)
     if (bkv == 0) bkv = ((a->lkv + 63) / 64 * 64 < (a->lkv + 127) / 128 * 128) ? 64 : 128;
-    if (bkv == 64) return launch_attn<1, 64, 2, 0>(ctx, p, a, stream);   // 3 CTAs per SM
+    if (bkv == 64) {
+      if (split_kv) return launch_attn<1, 64, 2, 0, true>(ctx, p, a, stream);
+      return launch_attn<1, 64, 2, 0>(ctx, p, a, stream);   // 3 CTAs per SM
+    }
     if (a->vt_ones) {
       const char* es = getenv("MDK_ATTN_STALE");   // read per call: tests switch kernels in-process
       const int stale = es ? atoi(es) : 0;         // off until measured on a B200
@@ -1385,8 +1388,18 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
   if (a->d <= 128) {
     const char* e = getenv("MDK_ATTN_BKV2");
     const int bkv2 = e ? atoi(e) : 128;
-    if (bkv2 == 64) return launch_attn<2, 64, 2, 0>(ctx, p, a, stream);   // 2 CTAs per SM
+    const char* esp2 = getenv("MDK_ATTN_SPLITKV");
+    const int split2 = esp2 ? atoi(esp2) : 0;
+    if (bkv2 == 64) {
+      if (split2) return launch_attn<2, 64, 2, 0, true>(ctx, p, a, stream);
+      return launch_attn<2, 64, 2, 0>(ctx, p, a, stream);   // 2 CTAs per SM
+    }
+    if (split2) return launch_attn<2, 128, 2, 0, true>(ctx, p, a, stream);
     return launch_attn<2, 128, 2, 0>(ctx, p, a, stream);
+  }
+  {
+    const char* esp3 = getenv("MDK_ATTN_SPLITKV");
+    if (esp3 && atoi(esp3)) return launch_attn<3, 64, 2, 0, true>(ctx, p, a, stream);
   }
   return launch_attn<3, 64, 2, 0>(ctx, p, a, stream);
 }
