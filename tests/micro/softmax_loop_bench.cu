@@ -14,13 +14,30 @@ __device__ __forceinline__ float ex2(float x) {
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// the attention kernel's half2 polynomial exp2 (csrc/attn_tc.cu::ex2_poly_h2)
+__device__ __forceinline__ uint32_t ex2_poly_h2(float x0, float x1) {
+  const __half2 lo = __floats2half2_rn(-15.0f, -15.0f);
+  const __half2 magic = __floats2half2_rn(1551.0f, 1551.0f);
+  __half2 x = __hmax2(__floats2half2_rn(x0, x1), lo);
+  const __half2 t = __hadd2(x, magic);
+  const __half2 n = __hsub2(t, magic);
+  const __half2 f = __hsub2(x, n);
+  __half2 pl = __hfma2(__floats2half2_rn(0.05517165f, 0.05517165f), f, __floats2half2_rn(0.24261113f, 0.24261113f));
+  pl = __hfma2(pl, f, __floats2half2_rn(0.69326097f, 0.69326097f));
+  pl = __hfma2(pl, f, __floats2half2_rn(0.99992806f, 0.99992806f));
+  const uint32_t tb = *reinterpret_cast<const uint32_t*>(&t);
+  const uint32_t eb = (tb & 0x001F001Fu) << 10;
+  const __half2 r = __hmul2(pl, *reinterpret_cast<const __half2*>(&eb));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ uint32_t pack(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // MODE 0: FFMA + EX2 + pack + STS (the kernel's mix)   1: + row max (FMNMX)   2: no STS   3: EX2 only (sum)
-// MODE 4: like 0 but every second pair on the FMA pipe (degree-3 polynomial, float)
+// MODE 4: like 0 but every second pair on the FMA pipe (degree-3 polynomial, float)   5: every fourth pair (25 %)
+// MODE 6: every second pair through the kernel's half2 polynomial (ex2_poly_h2)   7: every fourth pair, half2
 template <int MODE>
 __global__ void __launch_bounds__(384, 1) loop_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                        long long* __restrict__ cycles, int tiles, float scale) {
@@ -44,7 +61,11 @@ __global__ void __launch_bounds__(384, 1) loop_kernel(const float* __restrict__ 
         if (MODE == 1) mx[e] = fmaxf(mx[e], fmaxf(a, b));
         const float x0 = fmaf(a, scale, -m), x1 = fmaf(b, scale, -m);
         float p0, p1;
-        if (MODE == 4 && (e & 1)) {
+        if ((MODE == 6 && (e & 1)) || (MODE == 7 && e == 3)) {
+          pk[e] = ex2_poly_h2(x0, x1);
+          continue;
+        }
+        if ((MODE == 4 && (e & 1)) || (MODE == 5 && e == 3)) {
           // 2^x = 2^n * poly(f): magic-number rounding on the FMA pipe, exponent added with integer ops
           const float j0 = x0 + 12582912.f, j1 = x1 + 12582912.f;
           const float f0 = x0 - (j0 - 12582912.f), f1 = x1 - (j1 - 12582912.f);
@@ -119,5 +140,8 @@ int main() {
   run<0>("FFMA+EX2+F2FP+STS (kernel)", in, out, cyc, nsm);
   run<1>("kernel mix + row max", in, out, cyc, nsm);
   run<4>("kernel mix, 50% poly on FMA", in, out, cyc, nsm);
+  run<5>("kernel mix, 25% poly on FMA", in, out, cyc, nsm);
+  run<6>("kernel mix, 50% half2 poly", in, out, cyc, nsm);
+  run<7>("kernel mix, 25% half2 poly", in, out, cyc, nsm);
   return 0;
 }
