@@ -21,7 +21,7 @@ echo "== 2. every attention switch on the L0 self-attention shape (incl. MDK_ATT
 echo "== 2b. per-tile timeline of one CTA (which wait sets the period)" | tee -a $L
 ( MDK_TEST_UNVALIDATED=1 timeout 60 python tests/gpu_diag.py trace_attn 2>&1 | grep -E "trace|softmax warp|MMA warp|TMA warp|PASS|FAIL|EXC" ) | tee -a $L
 echo "== 3. softmax inner-loop ceiling (pure instruction mix)" | tee -a $L
-( timeout 15 ./build/softmax_loop_bench 2>&1 | tail -16 ) | tee -a $L
+( timeout 20 ./build/softmax_loop_bench 2>&1 | tail -28 ) | tee -a $L
 echo "== 4. step time with / without the split rings (only meaningful if 1. passed)" | tee -a $L
 for cfg in "MDK_X=0" "MDK_ATTN_SPLITKV=1" ; do
   ( env $cfg timeout 150 python bench.py --steps 8 --warmup 3 --skip-cpu-baseline --skip-reference-unet 2>> gpurun_out/r2_bench_stderr.log \
