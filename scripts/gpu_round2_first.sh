@@ -16,6 +16,8 @@ echo "== 1c. native VAE (written without a GPU)" | tee -a $L
 ( MDK_TEST_UNVALIDATED=1 timeout 180 python -m pytest tests/test_vae_gpu.py -q 2>&1 | tail -6 ) | tee -a $L
 echo "== 1d. the pipeline with every model stage native" | tee -a $L
 ( MDK_TEST_UNVALIDATED=1 timeout 180 python -m pytest tests/test_native_pipeline_gpu.py -q 2>&1 | tail -6 ) | tee -a $L
+echo "== 1e. VAE / CLIP timings at the bench resolution (only meaningful if 1b / 1c passed)" | tee -a $L
+( timeout 120 python tests/gpu_diag.py perf_vae_clip 2>&1 | grep -E "^perf|PASS|FAIL|EXC" ) | tee -a $L
 echo "== 2. every attention switch on the L0 self-attention shape (incl. MDK_ATTN_SPLITKV)" | tee -a $L
 ( MDK_TEST_UNVALIDATED=1 timeout 60 python tests/gpu_diag.py ab_attn_switches 2>&1 | grep -E "^perf|PASS|FAIL|EXC" ) | tee -a $L
 echo "== 2b. per-tile timeline of one CTA (which wait sets the period)" | tee -a $L

@@ -784,6 +784,39 @@ def check_vae_sd():
     return check_vae(synth.SD_VAE_CONFIG, 1, (256, 256), "SD")
 
 
+def perf_vae_clip():
+    """SD-size VAE at the bench resolution (one 768x768 frame: decode, encode) and CLIP ViT-L/14 (one image)."""
+    from mikudance_b200 import _lib, synth
+    from mikudance_b200.clip_vision import CLIPVisionModelWithProjection
+    from mikudance_b200.vae import AutoencoderKL
+    vcfg = synth.SD_VAE_CONFIG
+    vae = AutoencoderKL(**vcfg)
+    vae.load_state_dict(synth.synthetic_vae_state_dict(vcfg))
+    vae = vae.to(device=DEV, dtype=F16).eval()
+    z = (0.5 * synth._seeded_randn("vae_lat", (1, 4, 96, 96), 2)).half().to(DEV)
+    x = synth._seeded_randn("vae_img", (1, 3, 768, 768), 1).half().to(DEV)
+    eng = vae.engine()
+    for name, fn in (("decode 96x96 -> 768x768", lambda: eng.decode(z)), ("encode 768x768 -> 96x96", lambda: eng.encode_moments(x))):
+        n0 = _lib.launch_count()
+        fn()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - n0
+        ms = timeit(fn, iters=3, warm=1)
+        print(f"perf vae {name}: {ms:.2f} ms per frame, {launches} launches", flush=True)
+    ccfg = synth.CLIP_VITL14_CONFIG
+    clip = CLIPVisionModelWithProjection(**ccfg)
+    clip.load_state_dict(synth.synthetic_clip_state_dict(ccfg))
+    clip = clip.to(device=DEV, dtype=F16).eval()
+    px = synth.synthetic_pixel_values(ccfg, 1).half().to(DEV)
+    n0 = _lib.launch_count()
+    clip.image_prompt_embeds(px)
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - n0
+    ms = timeit(lambda: clip.image_prompt_embeds(px), iters=5, warm=1)
+    print(f"perf clip ViT-L/14 image_prompt_embeds: {ms:.2f} ms, {launches} launches", flush=True)
+    return True
+
+
 def perf_refunet():
     """Reference UNet at BASELINE config B's shape: 32 images (16 frames x 2 CFG branches) of 96x96 latents,
     SD-1.5 size, 257 CLIP tokens — the once-per-window cost of the hoisted writer."""
@@ -891,7 +924,7 @@ def trace_attn():
 
 
 CHECKS = {
-    "vae": check_vae, "vae_sd": check_vae_sd, "clip": check_clip, "clip_vitl14": check_clip_vitl14, "trace_attn": trace_attn, "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
+    "perf_vae_clip": perf_vae_clip, "vae": check_vae, "vae_sd": check_vae_sd, "clip": check_clip, "clip_vitl14": check_clip_vitl14, "trace_attn": trace_attn, "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
     "refunet_ops": check_refunet_ops, "refunet_tiny": check_refunet_tiny, "refunet_a": check_refunet_a,
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
