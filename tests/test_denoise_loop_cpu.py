@@ -120,3 +120,30 @@ def test_plan_ranks():
     assert plan_ranks(1, 2, False, True)["branch"] == -1          # no guidance: nothing to split
     assert plan_ranks(1, 3, True, True)["branch"] == -1           # odd world
     assert plan_ranks(0, 1, True, True)["branch"] == -1
+
+
+def test_denoise_loop_without_guidance_matches_oracle(monkeypatch):
+    """guidance_scale <= 1: one branch, every image reads its bank (pipeline_mikudance.py:397, 626-630, 670-674)."""
+    import ops_contract_cpu as K
+    from mikudance_b200 import synth
+    from mikudance_b200.denoise import DenoiseLoop
+    from mikudance_b200.scheduler import DDIMScheduler
+    from oracle.ddim_oracle import DDIMOracle
+    from oracle.pipeline_oracle import denoise_loop
+    K.install(monkeypatch)
+    cfg, m, sd = _build(K)
+    F_, h, w, steps = 3, 8, 8, 2
+    lat, ctx = synth.synthetic_inputs(cfg, 2, F_, h, w, lctx=5)
+    lat = lat[:1].half().contiguous()
+
+    def banks(wdw):
+        return synth.synthetic_banks(cfg, len(wdw), h, w, seed=500 + wdw[0])
+    loop = DenoiseLoop(m, DDIMScheduler(**KW), guidance_scale=1.0, context_frames=30, use_cuda_graph=False)
+    loop.prepare(lat.clone(), ctx[1:], steps, banks)
+    assert loop.nb == 1 and [len(x) for x in loop.windows] == [3]
+    got = loop.run().float()
+    with torch.no_grad():
+        want = denoise_loop({k: v.float() for k, v in sd.items()}, cfg, lat.float(), ctx.half().float(), steps, 1.0,
+                            banks, context_frames=30, scheduler=DDIMOracle(**KW))
+    rel = ((got - want).norm() / want.norm()).item()
+    assert rel < 8e-3, rel
