@@ -122,3 +122,33 @@ def test_forward_argument_errors(monkeypatch):
         reng.forward_api(torch.zeros(1, 22, 8, 8, dtype=torch.float16), 0, ctx)          # nn.InstanceNorm2d raises too
     with pytest.raises(ValueError, match="divisible by 8"):
         reng.forward_api(torch.zeros(1, 22, 20, 16, dtype=torch.float16), 0, ctx)
+
+
+def test_midup_fusion_blocks_only_read_mid_and_up_banks(monkeypatch):
+    """fusion_blocks="midup" (ReferenceAttentionControl's default): down blocks keep empty banks and fall back to plain
+    self-attention (mutual_mix_attention.py:169-172); mid / up blocks add theirs."""
+    from mikudance_b200 import synth
+    from mikudance_b200.engine import UNetEngine
+    from mikudance_b200.reference_control import ReferenceAttentionControl
+    from oracle import unet3d_oracle as O
+    K.install(monkeypatch)
+    cfg = synth.TINY_CONFIG
+    sd = synth.synthetic_state_dict(cfg, seed=1)
+    model = _unet3d(cfg)
+    model.load_state_dict(sd)
+    model = model.half().eval()
+    B, f, h, w = 2, 2, 8, 8
+    x, ctx = synth.synthetic_inputs(cfg, B, f, h, w, lctx=5)
+    banks = {k: v for k, v in synth.synthetic_banks(cfg, B * f, h, w).items() if not k.startswith("down_blocks")}
+    reader = ReferenceAttentionControl(model, mode="read", do_classifier_free_guidance=True, fusion_blocks="midup")
+    names = {id(m): n for n, m in model.named_modules()}
+    blocks = reader._blocks(model)
+    assert len(blocks) == 10 and not any(names[id(b)].startswith("down_blocks") for b in blocks)
+    for blk in blocks:
+        blk.bank = [banks[names[id(blk)].rsplit(".transformer_blocks", 1)[0]]]
+    eng = K.engine_on_cpu(UNetEngine, model)
+    y = eng.forward_api(x.half(), 19, ctx.half())
+    with torch.no_grad():
+        yo = O.unet3d_forward({k: v.float() for k, v in sd.items()}, cfg, x.half().float(), 19, ctx.half().float(),
+                              banks=banks, cfg_guidance=True)
+    assert _rel(y, yo) < 5e-3
