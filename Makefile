@@ -15,7 +15,7 @@ build/softmax_loop_bench: tests/micro/softmax_loop_bench.cu
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O3 -o $@ $<
 
-build/%.o: mikudance_b200/csrc/%.cu mikudance_b200/csrc/ptx.cuh mikudance_b200/csrc/host_common.h include/mdk.h
+build/%.o: mikudance_b200/csrc/%.cu mikudance_b200/csrc/ptx.cuh mikudance_b200/csrc/attn_common.cuh mikudance_b200/csrc/host_common.h include/mdk.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 

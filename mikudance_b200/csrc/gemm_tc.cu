@@ -729,12 +729,6 @@ static int launch_gemm(const mdk_ctx* ctx, const GemmParams& p, cudaStream_t str
   return 0;
 }
 
-// per-translation-unit copy of the try_wait time limit (see ptx.cuh); called by mdk_create
-int mdk_gemm_set_wait_ns(unsigned ns) {
-  MDK_CHECK_CUDA(cudaMemcpyToSymbol(mdk_c_wait_ns, &ns, sizeof(ns)));
-  return 0;
-}
-
 }  // namespace mdk
 
 extern "C" int mdk_gemm_geglu_block(void) { return 256; }

@@ -91,18 +91,6 @@ int mdk_create(int device, mdk_ctx** out) {
   if (prop.major != 10)
     return mdk::set_error("mdk_create: device %d is sm_%d%d; this library is sm_100a only", device,
                           prop.major, prop.minor);
-  {
-    // mbarrier try_wait time limit in ns (0 = system default, i.e. tight polling)
-    const char* e = getenv("MDK_WAIT_NS");
-    const unsigned ns = e ? static_cast<unsigned>(atoi(e)) : 0u;   // measured: a 1 ms limit (NANOSLEEP.SYNCS wake-ups) is 1-4 % slower than tight polling
-    int prev = 0;
-    MDK_CHECK_CUDA(cudaGetDevice(&prev));
-    MDK_CHECK_CUDA(cudaSetDevice(device));
-    int rc = mdk::mdk_gemm_set_wait_ns(ns);
-    if (rc == 0) rc = mdk::mdk_attn_set_wait_ns(ns);
-    cudaSetDevice(prev);
-    if (rc != 0) return rc;
-  }
   mdk_ctx* c = new mdk_ctx;
   c->device = device;
   c->num_sms = prop.multiProcessorCount;

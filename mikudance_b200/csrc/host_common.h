@@ -19,8 +19,6 @@ namespace mdk {
 
 int set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launch_count;
-int mdk_gemm_set_wait_ns(unsigned ns);   // gemm_tc.cu
-int mdk_attn_set_wait_ns(unsigned ns);   // attn_tc.cu
 inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
 
 #define MDK_CHECK_CUDA(expr)                                                              \

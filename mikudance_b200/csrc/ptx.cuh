@@ -44,57 +44,41 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait suspends the thread until the phase completes or a time limit expires.  With the
-// system-dependent default limit a waiting warp came back every ~100-200 cycles: ncu counted 8 M
-// polls (x ~8 instructions of loop around each) in one L0 attention launch, 19 % of all issued
-// instructions, competing with the softmax warps for issue slots and for the MIO queue the MUFU
-// instructions also go through.  With an explicit limit (mdk_c_wait_ns > 0, set per device from
-// MDK_WAIT_NS by mdk_create; the compiler emits TRYWAIT + NANOSLEEP.SYNCS) a wait is a few
-// instructions.  One copy of the constant per translation unit (no relocatable device code).
-static __constant__ uint32_t mdk_c_wait_ns = 0;
-
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait suspends the thread until the phase completes or a system-dependent time limit expires (a HW sleep,
+// not a poll: a waiting warp costs no issue slots).  An explicit suspend-time hint (round 1, MDK_WAIT_NS) gained
+// nothing and its constant-memory read sat in every wait, so it is gone.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar_addr, uint32_t parity) {
   uint32_t ok;
-  const uint32_t ns = mdk_c_wait_ns;
-  if (ns != 0u) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
-        "selp.b32 %0, 1, 0, P1;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P1;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
   return ok != 0;
 }
 
-// Bounded wait: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
-// The watchdog uses the SM-local clock64 (cheap) and only starts after a burst of plain polls.
+// Bounded wait: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.  The watchdog is a
+// clock64 comparison and a trap, nothing else: with a printf (a call with its argument marshalling) inlined at
+// every wait site the warp-specialised kernels were 40-100 KB of SASS — more than the 32 KB L1.5 instruction
+// cache — and a printf in an out-of-line function made ptxas spill the softmax registers around the call.
+// -DMDK_WAIT_DEBUG brings the message back for debugging a hang.
 #ifndef MDK_WAIT_LIMIT_CYCLES
 #define MDK_WAIT_LIMIT_CYCLES 8000000000ll  /* ~4 s at 2 GHz */
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#pragma unroll 1
-  for (int i = 0; i < 16; ++i)
-    if (mbar_try_wait(bar, parity)) return;
+  const uint32_t a = smem_u32(bar);
+  if (mbar_try_wait(a, parity)) return;
   const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xffu) == 0u && clock64() - t0 > MDK_WAIT_LIMIT_CYCLES) {
+  while (!mbar_try_wait(a, parity)) {
+    if (clock64() - t0 > MDK_WAIT_LIMIT_CYCLES) {
+#ifdef MDK_WAIT_DEBUG
       printf("mdk: mbarrier wait timed out (block %d,%d thread %d bar 0x%x parity %u)\n",
-             blockIdx.x, blockIdx.y, threadIdx.x, smem_u32(bar), parity);
+             blockIdx.x, blockIdx.y, threadIdx.x, a, parity);
+#endif
       __trap();
     }
   }
@@ -221,6 +205,20 @@ __device__ __forceinline__ void tc_mma_f16_ss(uint32_t d_tmem, uint64_t adesc, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T: A is a 128-lane x K tile of packed fp16 pairs in tensor memory (row r of A in
+// lane r, elements 2c and 2c+1 in the low / high half of 32-bit column c), B a K-major shared-memory tile.
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -352,6 +350,44 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
       "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+      "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16p(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};\n" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, uint32_t& a, uint32_t& b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() {

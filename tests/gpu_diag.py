@@ -858,9 +858,11 @@ def ab_attn_switches():
     vt2[:, :, :d] = rnd(nimg, C_, l, seed=12).to(F16).reshape(nimg, heads, d, l)
     vt2 = vt2.reshape(nimg, heads * dp, l)
     out = torch.empty_like(q)
-    names = ("MDK_ATTN_POLY", "MDK_ATTN_SK", "MDK_ATTN_PP", "MDK_ATTN_BKV", "MDK_ATTN_STALE", "MDK_ATTN_SPLITKV")
-    extra = ({"MDK_ATTN_SPLITKV": "1"}, {"MDK_ATTN_SPLITKV": "1", "MDK_ATTN_POLY": "1"}) \
-        if os.environ.get("MDK_TEST_UNVALIDATED", "0") == "1" else ()
+    names = ("MDK_ATTN_POLY", "MDK_ATTN_SK", "MDK_ATTN_PP", "MDK_ATTN_BKV", "MDK_ATTN_STALE", "MDK_ATTN_SPLITKV",
+             "MDK_ATTN_2S")
+    extra = ({"MDK_ATTN_SPLITKV": "1"}, {"MDK_ATTN_SPLITKV": "1", "MDK_ATTN_POLY": "1"},
+             {"MDK_ATTN_2S": "1"}, {"MDK_ATTN_2S": "1", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_2S": "1", "MDK_ATTN_POLY": "2"},
+             {"MDK_ATTN_2S": "2"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "2"})
     for env in ({}, {"MDK_ATTN_POLY": "1"}, {"MDK_ATTN_STALE": "1", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_SK": "1"},
                 {"MDK_ATTN_PP": "3"}, {"MDK_ATTN_BKV": "64"}) + extra + ({},):
         for n in names:
@@ -923,8 +925,55 @@ def trace_attn():
     return True
 
 
+def trace_attn_2s():
+    """Timeline of one CTA of the two-stream kernel (attn_2s.cu), P through shared memory (MDK_ATTN_2S=1) and P in
+    tensor memory (=2): median SM cycles between the hand-off points of a 128-key tile, per role."""
+    from mikudance_b200 import _lib
+    lib = _lib.load_library()
+    warm_gpu(0.5)
+    nimg, l, heads, d = 8, 9216, 8, 40
+    C_, dp = heads * d, d + 8
+    q = rnd(nimg * l, C_).to(F16)
+    k = rnd(nimg * l, C_, seed=11).to(F16)
+    vt2 = torch.ones(nimg, heads, dp, l, dtype=F16, device=DEV)
+    vt2[:, :, :d] = rnd(nimg, C_, l, seed=12).to(F16).reshape(nimg, heads, d, l)
+    vt2 = vt2.reshape(nimg, heads * dp, l)
+    out = torch.empty_like(q)
+    ntile = l // 128
+    for variant in ("1", "2"):
+        buf = torch.zeros(ntile * 16, dtype=torch.int64, device=DEV)
+        lib.mdk_attn_debug_trace(buf.data_ptr(), ntile)
+        os.environ["MDK_ATTN_TRACE"] = "1"
+        os.environ["MDK_ATTN_2S"] = variant
+        for _ in range(2):
+            ops.attention(q, k, vt2, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out, vt_head_rows=dp, vt_ones=True)
+        torch.cuda.synchronize()
+        os.environ.pop("MDK_ATTN_TRACE", None)
+        os.environ.pop("MDK_ATTN_2S", None)
+        lib.mdk_attn_debug_trace(None, 0)
+        t = buf.cpu().view(ntile, 16).double()
+        lo, hi = 8, ntile - 4
+
+        def med(a, b, shift_b=0):
+            x = t[lo:hi, a] - t[lo - shift_b:hi - shift_b, b]
+            return float(x.median())
+        print(f"trace attn2s [variant {variant}]: tile period {med(4, 4, 1):.0f} cycles (stream 1: {med(14, 14, 1):.0f}); "
+              f"stream 1 publishes {med(14, 4):.0f} cycles after stream 0")
+        for g, o in ((0, 0), (1, 10)):
+            print(f"  softmax stream {g}: wait S {med(o + 0, o + 4, 1):.0f} | TMEM load {med(o + 1, o + 0):.0f} | row max "
+                  f"{med(o + 2, o + 1):.0f} | exponentials {med(o + 3, o + 2):.0f} | P store + publish {med(o + 4, o + 3):.0f}")
+        if variant == "1":
+            print(f"  MMA thread 0: P(t) published -> seen {med(5, 4):.0f} | issue PV(t), QK(t+1), commits {med(6, 5):.0f} | "
+                  f"issued -> S(t+1) seen by softmax {float((t[lo + 1:hi + 1, 0] - t[lo:hi, 6]).median()):.0f} | "
+                  f"issued -> next unit seen landed {float((t[lo + 1:hi + 1, 7] - t[lo:hi, 6]).median()):.0f}")
+        else:
+            print(f"  stream 0 issuer: barrier passed -> PV(t), QK(t+1) issued and committed {med(6, 4):.0f} | "
+                  f"issued -> S(t+1) seen {float((t[lo + 1:hi + 1, 0] - t[lo:hi, 6]).median()):.0f}")
+    return True
+
+
 CHECKS = {
-    "perf_vae_clip": perf_vae_clip, "vae": check_vae, "vae_sd": check_vae_sd, "clip": check_clip, "clip_vitl14": check_clip_vitl14, "trace_attn": trace_attn, "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
+    "perf_vae_clip": perf_vae_clip, "vae": check_vae, "vae_sd": check_vae_sd, "clip": check_clip, "clip_vitl14": check_clip_vitl14, "trace_attn": trace_attn, "trace_attn_2s": trace_attn_2s, "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
     "refunet_ops": check_refunet_ops, "refunet_tiny": check_refunet_tiny, "refunet_a": check_refunet_a,
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
     "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,

@@ -1,8 +1,7 @@
 """GPU (-m gpu): the native CLIP image encoder against the fp32 oracle (itself pinned to
 transformers' implementation) and the golden vectors generated from transformers' model.
 
-STATUS: written after round 1's GPU budget was spent — not yet run on hardware, therefore opt-in
-(MDK_TEST_UNVALIDATED=1).  The host orchestration is covered on CPU by tests/test_clip_oracle.py; the kernels it
+STATUS: validated on a B200 in round 2 (profiles/r02_first_call.log); collected by the default -m gpu run.  The host orchestration is covered on CPU by tests/test_clip_oracle.py; the kernels it
 uses (GEMM with bias / row bias / transposed V^T segment, LayerNorm, attention at 257 tokens) are the validated
 ones, plus the new in-place QuickGELU."""
 import os
@@ -11,10 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MDK_TEST_UNVALIDATED", "0") != "1",
-                                 reason="native CLIP encoder not yet validated on hardware "
-                                        "(set MDK_TEST_UNVALIDATED=1 to run)")]
+pytestmark = pytest.mark.gpu
 
 import gpu_diag as D  # noqa: E402
 from conftest import GOLDEN  # noqa: E402

@@ -59,20 +59,13 @@ def test_flash_attention_tcgen05():
 
 @pytest.mark.parametrize("env", [{"MDK_ATTN_SK": "1"}, {"MDK_ATTN_PP": "3"}, {"MDK_ATTN_PP": "0"},
                                  {"MDK_ATTN_BKV": "64"}, {"MDK_ATTN_BKV": "128", "MDK_ATTN_PP": "0"},
-                                 {"MDK_ATTN_POLY": "1"}, {"MDK_ATTN_STALE": "1"}])
+                                 {"MDK_ATTN_POLY": "1"}, {"MDK_ATTN_STALE": "1"},
+                                 {"MDK_ATTN_2S": "1"}, {"MDK_ATTN_2S": "1", "MDK_ATTN_POLY": "1"},
+                                 {"MDK_ATTN_2S": "2"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "2"},
+                                 {"MDK_ATTN_SPLITKV": "1"}, {"MDK_ATTN_SPLITKV": "1", "MDK_ATTN_POLY": "1"}])
 def test_flash_attention_alternative_kernels(monkeypatch, env):
     """The kernels the dispatch heuristics do not pick by default (split-key, ping-pong for every
     head size, 64-key tiles) stay parity-green: the switches are read per call."""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    assert D.check_attn()
-
-
-@pytest.mark.skipif(__import__("os").environ.get("MDK_TEST_UNVALIDATED", "0") != "1",
-                    reason="split K / V^T ring kernel: written after round 1's GPU budget was spent, not yet run on "
-                           "hardware (set MDK_TEST_UNVALIDATED=1)")
-@pytest.mark.parametrize("env", [{"MDK_ATTN_SPLITKV": "1"}, {"MDK_ATTN_SPLITKV": "1", "MDK_ATTN_POLY": "1"}])
-def test_flash_attention_split_kv_rings(monkeypatch, env):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     assert D.check_attn()

@@ -2,8 +2,7 @@
 condition images, reference UNet (writer), denoising loop, VAE decode — against the same pipeline whose VAE / CLIP /
 writer are fp32 PyTorch modules built from the oracles (same weights).
 
-STATUS: written after round 1's GPU budget was spent — not yet run on hardware, therefore opt-in
-(MDK_TEST_UNVALIDATED=1)."""
+STATUS: validated on a B200 in round 2 (profiles/r02_first_call.log); collected by the default -m gpu run."""
 import os
 
 import numpy as np
@@ -11,10 +10,7 @@ import pytest
 import torch
 from torch import nn
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MDK_TEST_UNVALIDATED", "0") != "1",
-                                 reason="fully native pipeline not yet validated on hardware "
-                                        "(set MDK_TEST_UNVALIDATED=1 to run)")]
+pytestmark = pytest.mark.gpu
 
 import gpu_diag as D  # noqa: E402
 

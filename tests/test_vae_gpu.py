@@ -1,15 +1,12 @@
 """GPU (-m gpu): the native VAE against the fp32 restatement of diffusers' AutoencoderKL
 (oracle/vae_oracle.py — diffusers is absent here, so that restatement is itself unpinned).
 
-STATUS: written after round 1's GPU budget was spent — not yet run on hardware, therefore opt-in
-(MDK_TEST_UNVALIDATED=1).  The host orchestration is covered on CPU by tests/test_vae_oracle.py."""
+STATUS: validated on a B200 in round 2 (profiles/r02_first_call.log); collected by the default -m gpu run.  The host orchestration is covered on CPU by tests/test_vae_oracle.py."""
 import os
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MDK_TEST_UNVALIDATED", "0") != "1",
-                                 reason="native VAE not yet validated on hardware (set MDK_TEST_UNVALIDATED=1 to run)")]
+pytestmark = pytest.mark.gpu
 
 import gpu_diag as D  # noqa: E402
 
