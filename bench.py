@@ -176,49 +176,60 @@ def host_threads():
     return max(1, min(n, 64))
 
 
-def cpu_reference_sample(h, steps_cfg, reps, warm, budget_s=20.0):
-    """The reference algorithm (fp32 oracle restating the reference modules) on the host cores.
-    Bounded sample: ONE frame (both CFG branches = 2 images) of one UNet forward, at the largest latent
-    size of {config size, 64, 48, 32, 24, 16, 8} for which (reps + warm) forwards fit `budget_s` seconds
-    (predicted from an 8x8 calibration forward by the algorithmic-FLOP ratio); the result is scaled to
-    the config's size by the same ratio (stated in `sample`).  The loop also stops early once
-    2 x budget_s have elapsed.  A clip step costs `frames` such samples, the clip `num_steps * frames`."""
-    from mikudance_b200 import synth
-    from oracle import unet3d_oracle as O
-    cores = host_threads()
-    torch.set_num_threads(cores)
-    cfg = synth.SD15_CONFIG
-    sd = {k: v.float() for k, v in synth.synthetic_state_dict(cfg, seed=0).items()}
+REFERENCE_ROOT = "/root/reference"
 
-    def run(hs):
-        x, ctx = synth.synthetic_inputs(cfg, 2, 1, hs, hs, lctx=257)
-        banks = synth.synthetic_banks(cfg, 2, hs, hs)
+
+class CpuSample:
+    """The reference's CPU implementation of the path on a BOUNDED, FIXED sample of the workload: ONE frame (both
+    CFG branches = 2 images) of one UNet3DConditionModel forward at the config's own latent size (never a size
+    chosen at run time), fp32, on the host cores.  Runs the reference's unmodified modules through
+    oracle/diffusers_standin when /root/reference is mounted (kind "reference"; this container), else the oracle
+    port restating them (kind "port"; the GPU box).  One method for `cpu_baseline` and for `--impl reference`.
+    A clip step costs `frames` such samples (per window), the clip `num_inference_steps x frames`."""
+
+    def __init__(self, h):
+        from mikudance_b200 import synth
+        self.h = h
+        self.cores = host_threads()
+        torch.set_num_threads(self.cores)
+        cfg = synth.SD15_CONFIG
+        sd = {k: v.float() for k, v in synth.synthetic_state_dict(cfg, seed=0).items()}
+        self.x, self.ctx = synth.synthetic_inputs(cfg, 2, 1, h, h, lctx=257)
+        banks = synth.synthetic_banks(cfg, 2, h, h)
+        self.kind = "port"
+        if os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "models")) and os.environ.get("MDK_CPU_PORT", "0") != "1":
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "oracle", "diffusers_standin"))
+                sys.path.insert(1, REFERENCE_ROOT)
+                sys.path.insert(2, os.path.join(ROOT, "oracle"))
+                for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+                    del sys.modules[k]            # the repo's own src/ shims must not shadow the reference's
+                import make_golden
+                model = make_golden.build_reference_unet(cfg)
+                model.load_state_dict(sd)
+                make_golden.install_banks(model, banks, cfg, do_cfg=True)
+                self._fn = lambda: model(self.x, torch.tensor(499), encoder_hidden_states=self.ctx,
+                                         return_dict=False)[0]
+                self.kind = "reference"
+            except Exception as e:  # noqa: BLE001 — fall back to the port, say why
+                print(f"bench: reference modules unavailable ({type(e).__name__}: {e}); using the oracle port",
+                      file=sys.stderr)
+        if self.kind == "port":
+            from oracle import unet3d_oracle as O
+            self._fn = lambda: O.unet3d_forward(sd, cfg, self.x, 499, self.ctx, banks=banks, cfg_guidance=True)
+
+    def run(self):
+        """seconds of one sample (2 images of one UNet forward at latent h x h)"""
         with torch.no_grad():
             t0 = time.perf_counter()
-            O.unet3d_forward(sd, cfg, x, 499, ctx, banks=banks, cfg_guidance=True)
+            self._fn()
             return time.perf_counter() - t0
 
-    sizes = sorted({s_ for s_ in (h, 64, 48, 32, 24, 16, 8) if s_ <= h}, reverse=True)
-    fl = {hs: sum(per_image_flops(hs, 1).values()) for hs in sizes}
-    t_start = time.perf_counter()
-    t8 = run(8)                                        # calibration (also warms the thread pool)
-    hs = 8
-    for cand in sizes:
-        if (reps + warm) * t8 * fl[cand] / fl[8] <= budget_s:
-            hs = cand
-            break
-    times = []
-    for i in range(warm + reps):
-        dt = run(hs)
-        if i >= warm:
-            times.append(dt)
-        if time.perf_counter() - t_start > 2.0 * budget_s and times:
-            break
-    t = sum(times) / len(times) * fl[h] / fl[hs]      # seconds for 2 images at the config's size
-    fps = 1.0 / (steps_cfg * t)                        # frames / (steps * frames * t)
-    note = (f"latent {hs}x{hs}, {len(times)} timed forward(s), {cores} threads"
-            + ("" if hs == h else f", scaled to {h}x{h} by algorithmic FLOPs x{fl[h] / fl[hs]:.2f}"))
-    return t, fps, cores, note
+    def describe(self, n_timed):
+        what = ("the reference's own modules (src/models/unet_3d_mix.py ... through oracle/diffusers_standin)"
+                if self.kind == "reference" else "fp32 oracle restating the reference modules (oracle/unet3d_oracle.py)")
+        return (f"1 frame (2 CFG images) of one UNet forward at latent {self.h}x{self.h} per timed step, {n_timed} timed, "
+                f"{self.cores} threads, fp32, {what}")
 
 
 def time_reference_unet(cfg, dev, h, f_win, n_windows, num_steps, ms_step):
@@ -254,17 +265,51 @@ def time_reference_unet(cfg, dev, h, f_win, n_windows, num_steps, ms_step):
                      "runs it once per window per step")
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch (average over the launches of one step) from
-    the committed ncu launch list of `bench.py --ncu-step` (profiles/r01_ncu_step_traffic.json, written by
-    scripts/ncu_summarise.py); None when no capture is committed."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_step_traffic.json")) as f:
-            d = json.load(f)[kernel]
-        return dict(bytes_per_launch=d["dram_bytes"] / d["launches"], launches=d["launches"],
-                    dram_bytes_per_step=d["dram_bytes"], source=d.get("source", "ncu"))
-    except Exception:
-        return None
+def sharded_parity_check(dev, pg, world):
+    """N > 1 only, before the timed region: the frame-sharded loop (NCCL, CUDA graph) against the single-GPU loop on
+    identical inputs — tiny UNet3D, 2 DDIM steps, a window whose length does NOT divide by the rank count.  Every
+    rank holds the replicated latents; the worst rank is reported as `parity_vs_single`."""
+    import torch.distributed as dist
+    from mikudance_b200 import synth
+    from mikudance_b200.denoise import DenoiseLoop
+    from mikudance_b200.scheduler import DDIMScheduler
+    from mikudance_b200.unet_3d import UNet3DConditionModel
+    cfg = synth.TINY_CONFIG
+    m = UNet3DConditionModel(block_out_channels=cfg["block_out_channels"],
+                             cross_attention_dim=cfg["cross_attention_dim"], use_inflated_groupnorm=True,
+                             use_motion_module=True, motion_module_mid_block=True, motion_module_type="Vanilla",
+                             motion_module_kwargs=dict(temporal_position_encoding=True,
+                                                       temporal_position_encoding_max_len=32),
+                             unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+    m.load_state_dict(synth.synthetic_state_dict(cfg, seed=0))
+    m = m.to(device=dev, dtype=torch.float16).eval()
+    F_, h = 2 * world + 1, 16
+    lat, ctx = synth.synthetic_inputs(cfg, 2, F_, h, h, lctx=9)
+    lat = lat[:1].half()
+
+    def banks_for_window(wdw):
+        return synth.synthetic_banks(cfg, 2 * len(wdw), h, h, seed=300 + wdw[0])
+
+    res = {}
+    for name, g in (("single", None), ("sharded", pg)):
+        loop = DenoiseLoop(m, DDIMScheduler(**SCHED_KW), guidance_scale=GUIDANCE, context_frames=30,
+                           context_stride=1, context_overlap=8, process_group=g, use_cuda_graph=True)
+        loop.prepare(lat.to(dev).contiguous().clone(), ctx, 2, banks_for_window)
+        res[name] = loop.run().float()
+        mode = dict(cfg_split=loop.branch >= 0, exchange_ranks=loop.sub_world,
+                    frames_per_rank=[w["fl"] for w in loop.win])
+        torch.cuda.synchronize(dev)
+        loop.graph = None
+        dist.barrier()
+    rel = ((res["sharded"] - res["single"]).norm() / res["single"].norm()).reshape(1)
+    exact = torch.tensor([1.0 if torch.equal(res["sharded"], res["single"]) else 0.0], device=dev)
+    dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+    dist.all_reduce(exact, op=dist.ReduceOp.MIN)
+    m.engine().project_context(None)
+    del m
+    torch.cuda.empty_cache()
+    return dict(rel_l2=float(rel), bit_exact=bool(exact.item() > 0.5), frames=F_, steps=2, model="tiny UNet3D",
+                ranks=world, **mode)
 
 
 def main():
@@ -293,22 +338,33 @@ def main():
                     frames=F_, latent=h, num_inference_steps=num_steps, context_frames=ctx_frames,
                     images_per_unet_call=2 * min(F_, ctx_frames))
 
+    from mikudance_b200.context import get_context_scheduler
+    windows = [len(w) for w in get_context_scheduler("uniform")(0, num_steps, F_, ctx_frames, 1, 8)]
+    # `config` is identical in both arms (same workload); how each arm executes it is under `execution`
+    config = dict(workload, windows=windows,
+                  l2="working set >> L2: 2.6 GB weights + banks streamed every step")
+
     if args.impl == "reference":
         if rank != 0:
             return
-        reps = max(1, args.steps)
-        t, fps, cores, note = cpu_reference_sample(h, num_steps, reps, max(0, min(args.warmup, 1)), budget_s=90.0)
-        from mikudance_b200.context import get_context_scheduler
-        wins = [len(w) for w in get_context_scheduler("uniform")(0, num_steps, F_, ctx_frames, 1, 8)]
+        smp = CpuSample(h)
+        for _ in range(max(0, args.warmup)):
+            smp.run()
+        times = [smp.run() for _ in range(max(1, args.steps))]
+        t = sum(times) / len(times)          # measured seconds per timed step = per 1-frame sample
+        fps = 1.0 / (num_steps * t)          # 1 frame needs num_steps such UNet evaluations
         line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
-                    warmup=args.warmup, ms_per_step=t * F_ * 1e3, higher_is_better=True, scaling="strong",
-                    vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                    config=dict(workload, parallelism=f"host cores ({cores} threads), no GPU", windows=wins,
-                                l2="n/a (CPU)", cuda_graph=False),
-                    cpu_baseline=dict(value=fps, unit="frames/s", cores=cores, kind="port",
-                                      sample=f"1 of {F_} frames (2 CFG images) of one UNet forward per timed "
-                                             f"step ({note}), fp32 oracle of the reference modules; clip "
-                                             f"time extrapolated x{F_} frames x{num_steps} steps"),
+                    warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="strong",
+                    vs_baseline=None, dtype="f32", data="synthetic", impl="reference", config=config,
+                    execution=dict(parallelism=f"host cores ({smp.cores} threads), no GPU", cuda_graph=False,
+                                   step="one timed step = ONE frame of the clip (2 CFG images) through one UNet "
+                                        "forward; a clip step is `frames` of them per window"),
+                    cpu_baseline=dict(value=fps, unit="frames/s", cores=smp.cores, kind=smp.kind,
+                                      sample=smp.describe(len(times)),
+                                      extrapolated=dict(clip_step_s=t * sum(windows), clip_s=t * sum(windows) * num_steps,
+                                                        note="clip figures = sample x frame evaluations per step "
+                                                             "x steps; value itself is frames / (steps x measured "
+                                                             "sample time): frames/s is linear in frames")),
                     e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
@@ -326,6 +382,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
+    parity = sharded_parity_check(dev, pg, world) if world > 1 else None
     cfg = synth.SD15_CONFIG
     model = build_model(cfg, dev)
     sched = DDIMScheduler(**SCHED_KW)
@@ -384,19 +441,17 @@ def main():
 
     # ---- end to end with host buffers ----
     lat_host = lat0.clone().pin_memory()
-    ctx_host = ctx.to(torch.float16).pin_memory()
     out_host = torch.empty_like(lat_host).pin_memory()
 
     def e2e_step(i):
         loop.latents.copy_(lat_host, non_blocking=True)
-        loop.ctx.copy_(ctx_host, non_blocking=True)
         loop.step(i)
         out_host.copy_(loop.latents, non_blocking=True)
 
     for i in range(min(2, args.warmup)):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
-    h2d = lat_host.numel() * 2 + ctx_host.numel() * 2 + 8 + 16
+    h2d = lat_host.numel() * 2 + 8 + 16
     d2h = out_host.numel() * 2
 
     # ---- per-kernel profile of one eager step (CUDA events around every launch) ----
@@ -412,13 +467,12 @@ def main():
         kernels = prof.summary()
         shapes = prof.shapes(24)
         g = kernels.get("gemm_tc")
-        tr = ncu_traffic("gemm_tc_kernel")
         if g and g["ms"] > 0:
             ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
             roofline = dict(kernel="gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv, all launches of one step)",
                             bound="tensor", achieved=ach, peak=peaks["tflops_sustained"], unit="TFLOP/s",
                             frac=ach / peaks["tflops_sustained"],
-                            traffic=(tr["bytes_per_launch"] if tr else None), traffic_detail=tr,
+                            traffic=None,   # dram bytes are not measured inside this run (ncu: profiles/)
                             algorithmic_bytes_per_launch=g["bytes"] / g["n"],
                             launches=g["n"], share_of_step=g["ms"] / sum(k["ms"] for k in kernels.values()),
                             peak_source=peaks["source"] + ", sustained bf16 GEMM")
@@ -438,30 +492,33 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        t, fps, cores, note = cpu_reference_sample(h, num_steps, 1, 0, budget_s=15.0)
-        cpu = dict(value=fps, unit="frames/s", cores=cores, kind="port",
-                   sample=f"1 of {F_} frames (2 CFG images) of one config-{args.config} UNet forward "
-                          f"({note}; {t:.1f} s), fp32 oracle restating the reference modules; "
-                          f"extrapolated x{F_} frames x{num_steps} steps")
+        smp = CpuSample(h)
+        smp.run()                             # warm-up (thread pool, allocator)
+        t = smp.run()
+        cpu = dict(value=1.0 / (num_steps * t), unit="frames/s", cores=smp.cores, kind=smp.kind,
+                   sample=smp.describe(1) + f" ({t:.1f} s)",
+                   extrapolated=dict(clip_step_s=t * frame_evals, clip_s=t * frame_evals * num_steps))
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="f16", data="synthetic",
-                    config=dict(workload, parallelism=f"frames sharded over {world} GPU(s)",
-                                windows=[len(w) for w in loop.windows],
-                                l2="working set >> L2: 2.6 GB weights + banks streamed every step",
-                                cuda_graph=not args.no_graph),
+                    config=config,
+                    execution=dict(parallelism=f"frames sharded over {world} GPU(s)", cuda_graph=not args.no_graph),
                     clocks=clocks,
                     e2e=dict(value=F_ / (num_steps * ms_e2e / 1e3), unit="frames/s", ms_per_step=ms_e2e,
                              h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             note="reference banks (stand-in for the hoisted reference-UNet output) are "
-                                  "uploaded once per clip, like the weights"),
+                             note="per step: the latents in (pinned H2D) and out (D2H) + the step's scalars; the CLIP "
+                                  "context and the reference banks (stand-in for the hoisted reference-UNet "
+                                  "output) are uploaded once per clip, like the weights"),
                     gpu_launches=launches_per_step * args.steps, launches_per_step=launches_per_step,
-                    roofline=roofline,
-                    roofline_step=dict(bound="tensor", algorithmic_tflop_per_step=step_tflop,
-                                       achieved=step_ach, peak=peaks["tflops_sustained"], unit="TFLOP/s",
-                                       frac=(step_ach / peaks["tflops_sustained"]) if step_ach else None),
+                    roofline=dict(kernel="whole denoising step (all kernels; deduplicated algorithmic FLOPs, BASELINE.md)",
+                                  bound="tensor", achieved=step_ach, peak=peaks["tflops_sustained"], unit="TFLOP/s",
+                                  frac=(step_ach / peaks["tflops_sustained"]) if step_ach else None, traffic=None,
+                                  algorithmic_tflop_per_step=step_tflop,
+                                  peak_source=peaks["source"] + ", sustained bf16 GEMM"),
+                    roofline_gemm=roofline,
+                    parity_vs_single=parity,
                     reference_unet=refunet, kernels=kernels, top_shapes=shapes, cpu_baseline=cpu)
         print(json.dumps(line))
     if world > 1:

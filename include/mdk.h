@@ -177,6 +177,11 @@ typedef struct {
   int32_t silu;
   void* out;
   void* ws;
+  /* exchange layout (frame-sharded motion modules, mikudance_b200/sharding.py): out_chunk_pix > 0 writes pixel px
+   * of image i at row ((px / out_chunk_pix) * nimg + i) * out_chunk_pix + px % out_chunk_pix of an
+   * [out_chunks, nimg, out_chunk_pix, C] buffer — the send buffer of the frames -> pixels all-to-all, one
+   * contiguous block per destination rank (rows of pixels >= hw are not written).  0: [nimg, hw, C]. */
+  int32_t out_chunk_pix, out_chunks;
 } mdk_gn_args;
 
 int64_t mdk_groupnorm_ws_bytes(int32_t nimg, int32_t groups);
@@ -248,6 +253,14 @@ int mdk_latents_to_nhwc(mdk_ctx* ctx, const void* sample, void* out, int32_t b, 
 int mdk_pred_accumulate(mdk_ctx* ctx, const void* pred, float* acc, float* counter, int32_t b,
                         int32_t c, int32_t f_total, const int32_t* frame_idx, int32_t fl,
                         int32_t hw, int32_t cpad, void* stream);
+
+/* Back from the pixel-sharded layout of a frame-sharded motion module, fused with the module's residual add
+ * (src/models/motion_module.py:188): back [chunks, nimg, chunk_pix, C] (what the pixels -> frames all-to-all
+ * received: chunk d = pixels [d * chunk_pix, (d+1) * chunk_pix) of this rank's nimg images), x [nimg, hw, C]
+ *   out[i, px, :] = back[px / chunk_pix, i, px % chunk_pix, :] + x[i, px, :]        (fp32 add, one rounding)
+ * x == NULL: the layout change alone (bit-exact copy). */
+int mdk_unshard_add_f16(mdk_ctx* ctx, const void* back, const void* x, void* out, int32_t nimg, int32_t hw,
+                        int32_t chunk_pix, int32_t c, void* stream);
 
 /* Window average + classifier-free guidance + DDIM (eta = 0) update in one pass, fp32 math:
  *   eps = acc / counter;  g = eps_u + s (eps_c - eps_u)

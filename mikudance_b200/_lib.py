@@ -64,6 +64,7 @@ class GnArgs(C.Structure):
         ("nimg", c_int32), ("hw", c_int32), ("groups", c_int32), ("eps", c_float),
         ("gamma", c_void_p), ("beta", c_void_p), ("silu", c_int32),
         ("out", c_void_p), ("ws", c_void_p),
+        ("out_chunk_pix", c_int32), ("out_chunks", c_int32),
     ]
 
 
@@ -103,6 +104,7 @@ EXPORTS = [
     "mdk_cfg_ddim_step",
     "mdk_cond_to_nhwc_f16", "mdk_relu_f16", "mdk_man_ws_bytes", "mdk_man_modulate_f16",
     "mdk_attn_debug_trace", "mdk_quick_gelu_f16", "mdk_softmax_rows_f16", "mdk_im2col3x3_ex_f16",
+    "mdk_unshard_add_f16",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -142,6 +144,8 @@ def load_library() -> C.CDLL:
                                         c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p]
     lib.mdk_pred_accumulate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                         c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p]
+    lib.mdk_unshard_add_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                        c_int32, c_void_p]
     lib.mdk_cfg_ddim_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                       c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.mdk_cond_to_nhwc_f16.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int32] * 9 + [c_void_p]

@@ -188,6 +188,39 @@ static inline int grid_for(long long total, int block, int num_sms) {
   return static_cast<int>(g);
 }
 
+
+// out[i, px, :] = back[px / pp, i, px % pp, :] (+ x[i, px, :])   (16-byte vectors, fp32 add; x may be NULL)
+__global__ void unshard_add_kernel(const __half* __restrict__ back, const __half* __restrict__ x,
+                                   __half* __restrict__ out, int nimg, int hw, int pp, int cv) {
+  const long long total = static_cast<long long>(nimg) * hw * cv;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(t % cv);
+    const long long row = t / cv;
+    const int px = static_cast<int>(row % hw);
+    const int img = static_cast<int>(row / hw);
+    const int d = px / pp;
+    const long long brow = (static_cast<long long>(d) * nimg + img) * pp + (px - d * pp);
+    const uint4 a = *reinterpret_cast<const uint4*>(back + (brow * cv + v) * 8);
+    if (x == nullptr) {   // pure layout change (bit-exact)
+      *reinterpret_cast<uint4*>(out + (row * cv + v) * 8) = a;
+      continue;
+    }
+    const uint4 b = *reinterpret_cast<const uint4*>(x + (row * cv + v) * 8);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __half22float2(ah[e]), fb = __half22float2(bh[e]);
+      const __half2 r = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+      ow[e] = *reinterpret_cast<const uint32_t*>(&r);
+    }
+    *reinterpret_cast<uint4*>(out + (row * cv + v) * 8) = o;
+  }
+}
+
 }  // namespace mdk
 
 using namespace mdk;
@@ -232,6 +265,21 @@ extern "C" int mdk_latents_to_nhwc(mdk_ctx* ctx, const void* sample, void* out, 
   latents_to_nhwc_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, stream>>>(
       static_cast<const __half*>(sample), static_cast<__half*>(out), b, b_src, c, f_total, frame_idx,
       fl, hw, cpad);
+  count_launch();
+  MDK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mdk_unshard_add_f16(mdk_ctx* ctx, const void* back, const void* x, void* out, int32_t nimg,
+                                   int32_t hw, int32_t chunk_pix, int32_t c, void* stream_) {
+  using namespace mdk;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MDK_REQUIRE(ctx && back && out, "mdk_unshard_add_f16: null argument");
+  MDK_REQUIRE(c % 8 == 0 && c > 0 && chunk_pix > 0 && nimg > 0 && hw > 0, "mdk_unshard_add_f16: bad shape");
+  const long long total = static_cast<long long>(nimg) * hw * (c / 8);
+  unshard_add_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, stream>>>(
+      static_cast<const __half*>(back), static_cast<const __half*>(x), static_cast<__half*>(out), nimg, hw,
+      chunk_pix, c / 8);
   count_launch();
   MDK_CHECK_CUDA(cudaGetLastError());
   return 0;

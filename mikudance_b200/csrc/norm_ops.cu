@@ -26,6 +26,9 @@ struct GnParams {
   float* ws;  // [nimg, GN_MAX_CHUNKS, groups, 2] per-CTA partial (sum, sumsq)
   int pix_per_cta;
   int nchunks;
+  int out_chunk_pix;   // > 0: exchange layout [chunk, nimg_total, out_chunk_pix, C] (see mdk.h)
+  int nimg_total;      // images of the whole call (the launch may cover a sub-range starting at img0)
+  int img0;
 };
 
 __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
@@ -195,7 +198,12 @@ __global__ void gn_apply_kernel(const GnParams p) {
           if (p.silu) y = __fdividef(y, 1.0f + __expf(-y));
           v[e] = y;
         }
-        store8(p.out + (static_cast<long long>(img) * p.hw + pp) * p.C + ch, v);
+        long long orow = static_cast<long long>(img) * p.hw + pp;
+        if (p.out_chunk_pix > 0) {
+          const int d = pp / p.out_chunk_pix;
+          orow = (static_cast<long long>(d) * p.nimg_total + (p.img0 + img)) * p.out_chunk_pix + (pp - d * p.out_chunk_pix);
+        }
+        store8(p.out + orow * p.C + ch, v);
       }
     }
   }
@@ -452,6 +460,12 @@ extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* strea
   p.silu = a->silu;
   p.out = static_cast<__half*>(a->out);
   p.ws = static_cast<float*>(a->ws);
+  p.out_chunk_pix = a->out_chunk_pix;
+  p.nimg_total = a->nimg;
+  p.img0 = 0;
+  MDK_REQUIRE(a->out_chunk_pix == 0 || (a->out_chunk_pix > 0 && a->out_chunks > 0 &&
+                                        static_cast<long long>(a->out_chunk_pix) * a->out_chunks >= a->hw),
+              "mdk_groupnorm_f16: exchange layout %d x %d does not cover hw=%d", a->out_chunks, a->out_chunk_pix, a->hw);
   const int V = C / 8;
   // blockDim.x = V exactly (not rounded up to a warp multiple): thread (x, y) reads vector x of pixel
   // y, so with a single source the linear thread id walks memory contiguously and every lane of
@@ -491,7 +505,8 @@ extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* strea
     q.nimg = ni;
     q.x0 = p.x0 + static_cast<long long>(i0) * a->hw * a->c0;
     if (p.x1) q.x1 = p.x1 + static_cast<long long>(i0) * a->hw * a->c1;
-    q.out = p.out + static_cast<long long>(i0) * a->hw * C;
+    q.out = (p.out_chunk_pix > 0) ? p.out : p.out + static_cast<long long>(i0) * a->hw * C;
+    q.img0 = i0;
     q.ws = p.ws + static_cast<long long>(i0) * GN_MAX_CHUNKS * a->groups * 2;
     // enough CTAs to fill the machine a few times over, at least one pixel row of work each
     int chunks = (ctx->num_sms * 8 + ni - 1) / ni;

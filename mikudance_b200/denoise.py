@@ -10,9 +10,10 @@ captured graph is replayed for every step; per step the host only writes 1 + 4 s
 Frame sharding: rank r of G runs the UNet on frames [r*fl, (r+1)*fl) of every window (both CFG
 branches); the motion modules exchange frames<->pixels (or all-gather K/V) over NCCL (engine._motion);
 the window accumulators are summed across ranks once per step (2.4 MB at 768x768x16f) and the DDIM
-update is replicated.  With MDK_CFG_SPLIT=1 (even G, guidance on; off by default until it has run on
-NCCL) the two CFG branches go to the two halves of the ranks instead (sharding.plan_ranks): the
-motion-module exchange then spans G/2 ranks — none at G = 2.
+update is replicated.  With an even G and guidance on (MDK_CFG_SPLIT=0 switches it off) the two CFG branches go
+to the two halves of the ranks instead (sharding.plan_ranks): the motion-module exchange then spans G/2 ranks —
+none at G = 2.  Windows need not divide by the rank count (sharding.frame_split: 30 frames = 8 + 8 + 7 + 7).
+Banks keep only the cond half (the uncond images never read them): 0.83 GB per 16-frame window at 768x768.
 """
 from __future__ import annotations
 
@@ -48,7 +49,7 @@ class DenoiseLoop:
         else:
             self.world, self.rank = 1, 0
         import os
-        plan = plan_ranks(self.rank, self.world, self.do_cfg, os.environ.get("MDK_CFG_SPLIT", "0") == "1")
+        plan = plan_ranks(self.rank, self.world, self.do_cfg, os.environ.get("MDK_CFG_SPLIT", "1") == "1")
         self.branch, self.sub_rank, self.sub_world = plan["branch"], plan["sub_rank"], plan["sub_world"]
         if self.branch >= 0:
             import torch.distributed as dist
@@ -78,6 +79,9 @@ class DenoiseLoop:
         _, self.c, self.F, self.h, self.w = latents.shape
         self.nb = 2 if self.do_cfg else 1
         self.ctx = ctx.to(device=dev, dtype=F16).contiguous()
+        # the context this rank's UNet calls see (CFG split: one branch); its cross-attention K / V^T once per clip
+        self.ctx_run = self.ctx if self.branch < 0 else self.ctx[self.branch:self.branch + 1]
+        self.eng.project_context(self.ctx_run)
         self.scheduler.set_timesteps(num_inference_steps)
         self.timesteps = [int(t) for t in self.scheduler.timesteps]
         # the reference always calls the scheduler with step=0 (pipeline_mikudance.py:603-612)
@@ -86,6 +90,11 @@ class DenoiseLoop:
         self.win = []
         for wdw in self.windows:
             L = len(wdw)
+            if len(set(int(i) for i in wdw)) != L:
+                # the reference's indexed assignment (pipeline_mikudance.py:662-664) is last-write-wins with the
+                # counter bumped once; the accumulate kernel adds without atomics and assumes distinct frames
+                raise NotImplementedError(f"context window {list(wdw)} repeats a frame (context_stride > 1 with "
+                                          "wrap-around): not supported")
             mine, lo = shard_window(wdw, self.sub_rank, self.sub_world)
             fl = len(mine)
             idx = torch.tensor(mine, dtype=torch.int32, device=dev)
@@ -93,11 +102,10 @@ class DenoiseLoop:
             if banks_for_window is not None:
                 full = banks_for_window(wdw)
                 if full is not None and self.branch != 0:          # the uncond branch never reads a bank
-                    banks = {k: slice_bank(v, self.nb, L, self.sub_rank, self.sub_world)
-                             .to(device=dev, dtype=F16) for k, v in full.items()}
-                    if self.branch == 1:                           # cond branch only: second half of (b fl)
-                        banks = {k: v[fl:] for k, v in banks.items()}
-                    banks = {k: v.contiguous() for k, v in banks.items()}
+                    # keep the cond half of (b fl) only: the rows that are read (uncond images never see a bank)
+                    r0 = fl if self.do_cfg else 0
+                    banks = {k: slice_bank(v, self.nb, L, self.sub_rank, self.sub_world)[r0:]
+                             .to(device=dev, dtype=F16).contiguous() for k, v in full.items()}
             self.win.append(dict(frames=wdw, idx=idx, fl=fl, f_off=lo, L=L, banks=banks))
         self.acc = torch.zeros((self.nb, self.c, self.F, self.h, self.w), dtype=torch.float32, device=dev)
         self.counter = torch.zeros(self.F, dtype=torch.float32, device=dev)
@@ -123,14 +131,14 @@ class DenoiseLoop:
             if br < 0:
                 x_in = ops.latents_to_nhwc(self.latents, b=self.nb, frame_idx=wd["idx"], fl=fl,
                                            cpad=eng.cin_pad)
-                pred = eng.run(x_in, self.nb, fl, self.h, self.w, self.ctx, wd["banks"],
+                pred = eng.run(x_in, self.nb, fl, self.h, self.w, self.ctx_run, wd["banks"],
                                n_uncond=(fl if n_unc_all else 0), f_off=wd["f_off"], f_total=wd["L"])
                 ops.pred_accumulate(pred, self.acc, self.counter, frame_idx=wd["idx"], fl=fl)
             else:
                 # CFG split: this rank evaluates ONE branch; its row of the accumulator gets the prediction,
                 # the other row stays zero until the all-reduce; the uncond ranks own the frame counter
                 x_in = ops.latents_to_nhwc(self.latents, b=1, frame_idx=wd["idx"], fl=fl, cpad=eng.cin_pad)
-                pred = eng.run(x_in, 1, fl, self.h, self.w, self.ctx[br:br + 1], wd["banks"],
+                pred = eng.run(x_in, 1, fl, self.h, self.w, self.ctx_run, wd["banks"],
                                n_uncond=(fl if br == 0 else 0), f_off=wd["f_off"], f_total=wd["L"])
                 ops.pred_accumulate(pred, self.acc[br:br + 1], self.counter if br == 0 else None,
                                     frame_idx=wd["idx"], fl=fl)

@@ -225,6 +225,9 @@ class UNetEngine:
         self.t_dev = torch.zeros(1, dtype=torch.int64, device=dev)
 
     # ------------------------------------------------------------------------------------------
+    _ctx_kv: dict = {}
+    _ctx_key = None
+
     def set_process_group(self, pg, rank: int, world: int):
         self.pg, self.rank, self.world = pg, rank, world
 
@@ -243,6 +246,33 @@ class UNetEngine:
             assert x1 is None
             sc = x0
         return ops.gemm(h, r.w2, bias=r.b2, residual=sc, conv=(N, H, W))
+
+    def _project_ctx_block(self, s, ctx2d, nctx, lctx):
+        lcp = (lctx + 7) // 8 * 8
+        k2 = torch.empty((nctx * lctx, s.c), dtype=F16, device=self.dev)
+        vt2 = torch.empty((nctx, s.c, lcp), dtype=F16, device=self.dev)
+        ops.gemm(ctx2d, s.wkv2, outs=[k2, vt2], trans=[False, True], trans_rows=lctx)
+        return k2, vt2
+
+    def spatial_entries(self):
+        out = []
+        for e in list(self.down) + list(self.up):
+            out.extend(e.att or [])
+        out.append(self.mid_att)
+        return out
+
+    def project_context(self, ctx: Optional[torch.Tensor]) -> None:
+        """K / V^T of the CLIP context [nctx, L, D] for every spatial block, once (the 257-token
+        context is constant over the denoising loop).  run() uses them whenever it is called with this very tensor
+        (same storage and shape); the caller re-projects after changing its contents.  None drops the cache."""
+        self._ctx_kv, self._ctx_key = {}, None
+        if ctx is None:
+            return
+        nctx, lctx, dctx = ctx.shape
+        ctx2d = ctx.reshape(nctx * lctx, dctx)
+        for s in self.spatial_entries():
+            self._ctx_kv[s.name] = self._project_ctx_block(s, ctx2d, nctx, lctx)
+        self._ctx_key = (ctx2d.data_ptr(), nctx, lctx)
 
     def _ff(self, o, h, lnw, lnb):
         n = ops.layernorm(h, lnw, lnb)
@@ -270,7 +300,10 @@ class UNetEngine:
             vt.view(N, self.heads, dp, lp)[:, :, d:].fill_(1.0)
         if bank is not None:
             r0 = n_uncond * hw
-            n1, kvin = ops.layernorm(h, s.ln1w, s.ln1b, add=bank[r0:], add_row0=r0)
+            # banks hold the rows that are read: the cond images only (the CFG uncond half never sees the bank,
+            # mutual_mix_attention.py:181-201); a full [(N hw), C] bank (the reference's layout) is sliced here
+            bank_c = bank if bank.shape[0] == (N - n_uncond) * hw else bank[r0:]
+            n1, kvin = ops.layernorm(h, s.ln1w, s.ln1b, add=bank_c, add_row0=r0)
             if n_uncond > 0:     # CFG uncond half: plain self-attention (mutual_mix_attention.py:181-201)
                 ops.gemm(n1[:r0], s.wqkv, outs=[q[:r0], k[:r0], vt[:n_uncond]],
                          trans=[False, False, True], trans_rows=hw, trans_head=th)
@@ -285,13 +318,15 @@ class UNetEngine:
         a = ops.attention(q, k, vt, nimg=N, lq=hw, lkv=hw, heads=self.heads, d=d, vt_head_rows=dp,
                           vt_ones=ones)
         h = ops.gemm(a, s.wo, bias=s.bo, residual=h)
-        # CLIP cross-attention (mutual_mix_attention.py:206-220); K/V of the context once per call
+        # CLIP cross-attention (mutual_mix_attention.py:206-220); K / V^T of the context: projected once per clip
+        # by project_context() (the denoising loop's context is constant), else per call
         n2 = ops.layernorm(h, s.ln2w, s.ln2b)
         q2 = ops.gemm(n2, s.wq2)
-        lcp = (lctx + 7) // 8 * 8
-        k2 = torch.empty((nctx * lctx, C), dtype=F16, device=dev)
-        vt2 = torch.empty((nctx, C, lcp), dtype=F16, device=dev)
-        ops.gemm(ctx2d, s.wkv2, outs=[k2, vt2], trans=[False, True], trans_rows=lctx)
+        cached = self._ctx_kv.get(s.name) if self._ctx_key == (ctx2d.data_ptr(), nctx, lctx) else None
+        if cached is not None:
+            k2, vt2 = cached
+        else:
+            k2, vt2 = self._project_ctx_block(s, ctx2d, nctx, lctx)
         a2 = ops.attention(q2, k2, vt2, nimg=N, lq=hw, lkv=lctx, heads=self.heads, d=d,
                            kv_div=max(1, N // nctx))
         h = ops.gemm(a2, s.wo2, bias=s.bo2, residual=h)
@@ -299,25 +334,38 @@ class UNetEngine:
         return ops.gemm(h, s.pout_w, bias=s.pout_b, residual=x)
 
     def _motion_a2a(self, o, x, N, H, W, nb, fl, f_total):
-        """Frame-sharded motion module with two all-to-all exchanges (frame-sharded <-> pixel-sharded)
-        instead of an all-gather of K/V per temporal attention: everything between GroupNorm (per
-        image) and proj_out (per token) is per pixel, so once each rank holds ALL frames of hw/G
-        pixels the temporal transformer needs no further communication.  Volume per module:
-        2 * (G-1)/G of the local activation (4-16x less than the K/V all-gather)."""
-        from .sharding import frames_to_pixels, pixels_per_rank, pixels_to_frames
+        """Frame-sharded motion module with two all-to-all exchanges (frame-sharded <-> pixel-sharded) per CFG
+        branch instead of an all-gather of K/V per temporal attention: everything between GroupNorm (per image)
+        and proj_out (per token) is per pixel, so once each rank holds ALL frames of hw/G pixels the temporal
+        transformer needs no further communication.  Volume per module: 2 * (G-1)/G of the local activation
+        (4-16x less than the K/V all-gather).  No layout copies around the exchanges: GroupNorm
+        writes the send buffer ([G(dst), fl, pp, C], `chunks=`), the received blocks already are frame-major
+        ([F, pp, C] per branch, also with an uneven frame split), and one `unshard` kernel per branch puts the
+        returning pixel chunks side by side (pure data movement: the sharded result equals the single-GPU one
+        bit for bit)."""
+        from .sharding import frame_split, frames_to_pixels, pixels_per_rank, pixels_to_frames
         hw, C, G = H * W, o.c, self.world
+        counts = frame_split(f_total, G)
+        assert counts[self.rank] == fl, (counts, self.rank, fl)
         pp = pixels_per_rank(hw, G)
         d = C // self.mheads
-        g = ops.groupnorm(x, o.gnw, o.gnb, nimg=N, hw=hw, groups=self.groups, eps=1e-6, silu=False)
-        h = frames_to_pixels(g, nb, fl, hw, G, self.pg)                          # rows [(b f_total) pp]
-        h = ops.gemm(h, o.pin_w, bias=o.pin_b)
+        recv = torch.empty((nb, f_total * pp, C), dtype=F16, device=self.dev)
+        for b in range(nb):
+            send = ops.groupnorm(x[b * fl * hw:(b + 1) * fl * hw], o.gnw, o.gnb, nimg=fl, hw=hw, groups=self.groups,
+                                 eps=1e-6, silu=False, chunks=(G, pp))
+            frames_to_pixels(send, recv[b], counts, pp, self.rank, self.pg)
+        h = ops.gemm(recv.view(nb * f_total * pp, C), o.pin_w, bias=o.pin_b)    # rows [(b f_total) pp]
         for e in o.att:
             n = ops.layernorm(h, e.lnw, e.lnb)
             qkv = ops.gemm(n, e.wqkv, row_bias=e.pe_qkv[:f_total], row_div=pp)
             a = ops.temporal_attention(qkv, nb=nb, f_q=f_total, npix=pp, heads=self.mheads, d=d)
             h = ops.gemm(a, e.wo, bias=e.bo, residual=h)
         h = self._ff(o, h, o.ffnw, o.ffnb)
-        hb = pixels_to_frames(h, nb, fl, hw, G, self.pg)
+        hb = torch.empty((nb * fl * hw, C), dtype=F16, device=self.dev)
+        for b in range(nb):
+            back = torch.empty((G * fl * pp, C), dtype=F16, device=self.dev)
+            pixels_to_frames(h[b * f_total * pp:(b + 1) * f_total * pp], back, counts, pp, self.rank, self.pg)
+            ops.unshard(back, nimg=fl, hw=hw, chunk_pix=pp, out=hb[b * fl * hw:(b + 1) * fl * hw])
         return ops.gemm(hb, o.pout_w, bias=o.pout_b, residual=x)
 
     def _motion(self, o, x, N, H, W, nb, fl, f_off, f_total):
@@ -340,6 +388,9 @@ class UNetEngine:
                 kv = torch.empty((N * hw, 2 * C), dtype=F16, device=self.dev)
                 ops.gemm(n, e.wqkv, outs=[qb, kv[:, :C], kv[:, C:]], row_bias=pe_rows, row_div=hw)
                 if self.world > 1:
+                    if f_total != fl * self.world:
+                        raise NotImplementedError("the K/V all-gather mode needs an even frame split "
+                                                  "(use shard_mode='a2a')")
                     kv_all = torch.empty((self.world * N * hw, 2 * C), dtype=F16, device=self.dev)
                     dist.all_gather_into_tensor(kv_all, kv, group=self.pg)   # NCCL over NVLink
                 else:

@@ -222,13 +222,21 @@ def temporal_attention(qkv: torch.Tensor, *, nb: int, f_q: int, npix: int, heads
 
 def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, nimg: int, hw: int,
               groups: int, eps: float, silu: bool, x1: Optional[torch.Tensor] = None,
-              out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None,
+              chunks: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """chunks = (n_chunks, chunk_pix): write the exchange layout [n_chunks, nimg, chunk_pix, C] (the send buffer of
+    the frames -> pixels all-to-all; rows of pixels >= hw stay zero) instead of [nimg * hw, C]."""
     _chk16(x0, "x0")
     dev = x0.device
     c0 = x0.shape[1]
     c1 = x1.shape[1] if x1 is not None else 0
     if out is None:
-        out = torch.empty((nimg * hw, c0 + c1), dtype=F16, device=dev)
+        if chunks is None:
+            out = torch.empty((nimg * hw, c0 + c1), dtype=F16, device=dev)
+        elif chunks[0] * chunks[1] == hw:
+            out = torch.empty((chunks[0] * nimg * chunks[1], c0 + c1), dtype=F16, device=dev)
+        else:
+            out = torch.zeros((chunks[0] * nimg * chunks[1], c0 + c1), dtype=F16, device=dev)
     if ws is None:
         ws = torch.empty((load_library().mdk_groupnorm_ws_bytes(nimg, groups),), dtype=torch.uint8, device=dev)
     a = GnArgs()
@@ -238,6 +246,8 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, nimg
     a.nimg, a.hw, a.groups, a.eps = nimg, hw, groups, eps
     a.gamma, a.beta, a.silu = ptr(gamma), ptr(beta), 1 if silu else 0
     a.out, a.ws = ptr(out), ptr(ws)
+    if chunks is not None:
+        a.out_chunks, a.out_chunk_pix = chunks
     _run("groupnorm", 0.0, 3.0 * 2 * nimg * hw * (c0 + c1),
          lambda: load_library().mdk_groupnorm_f16(get_ctx(dev), C.byref(a), cur_stream(dev)),
          "mdk_groupnorm_f16")
@@ -329,6 +339,25 @@ def pred_accumulate(pred: torch.Tensor, acc: torch.Tensor, counter: Optional[tor
                                                     ptr(counter), b, c, F, ptr(frame_idx), fl, h * w,
                                                     pred.shape[1], cur_stream(pred.device)),
          "mdk_pred_accumulate")
+
+
+def unshard(back: torch.Tensor, *, nimg: int, hw: int, chunk_pix: int, x: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i, px] = back[px // chunk_pix, i, px % chunk_pix] (+ x[i, px]): the way back from the pixel-sharded layout
+    of a frame-sharded motion module ([chunks, nimg, chunk_pix, C] -> [nimg * hw, C]), optionally fused with a
+    residual add."""
+    _chk16(back, "back")
+    c = back.shape[1]
+    assert back.shape[0] >= nimg * hw and back.is_contiguous()
+    if x is not None:
+        _chk16(x, "x")
+        assert x.shape == (nimg * hw, c) and x.is_contiguous()
+    if out is None:
+        out = torch.empty((nimg * hw, c), dtype=F16, device=back.device)
+    _run("latent_glue", 0.0, (6.0 if x is not None else 4.0) * out.numel(),
+         lambda: load_library().mdk_unshard_add_f16(get_ctx(back.device), ptr(back), ptr(x), ptr(out), nimg, hw,
+                                                    chunk_pix, c, cur_stream(back.device)), "mdk_unshard_add_f16")
+    return out
 
 
 def cfg_ddim_step(acc: torch.Tensor, counter: torch.Tensor, latents: torch.Tensor,

@@ -32,61 +32,65 @@ def plan_ranks(rank: int, world: int, do_cfg: bool, cfg_split: bool) -> Dict[str
     return dict(branch=-1, sub_rank=rank, sub_world=world)
 
 
+def frame_split(length: int, world: int) -> List[int]:
+    """Frames of a `length`-frame window per rank: as even as possible, the first length % world ranks carry one
+    more (a 30-frame window over 8 GPUs = 6 x 4 + 2 x 3, over 4 GPUs = 2 x 8 + 2 x 7)."""
+    if length < world:
+        raise ValueError(f"a window of {length} frames cannot be sharded over {world} GPUs (fewer frames than ranks)")
+    base, rem = divmod(length, world)
+    return [base + 1] * rem + [base] * (world - rem)
+
+
 def shard_window(window: Sequence[int], rank: int, world: int) -> Tuple[List[int], int]:
     """(frames of `window` owned by `rank`, offset of the first one inside the window)."""
-    L = len(window)
-    if L % world != 0:
-        raise ValueError(f"a window of {L} frames cannot be split evenly over {world} GPUs; "
-                         "choose context_frames divisible by the GPU count")
-    fl = L // world
-    lo = rank * fl
-    return list(window[lo:lo + fl]), lo
+    counts = frame_split(len(window), world)
+    lo = sum(counts[:rank])
+    return list(window[lo:lo + counts[rank]]), lo
 
 
 def slice_bank(bank: torch.Tensor, nb: int, window_len: int, rank: int, world: int) -> torch.Tensor:
     """bank [(nb * L), hw, C] for the whole window -> this rank's [(nb * fl), hw, C] (b-major)."""
-    fl = window_len // world
+    counts = frame_split(window_len, world)
+    lo, fl = sum(counts[:rank]), counts[rank]
     hw, C = bank.shape[-2], bank.shape[-1]
-    return bank.reshape(nb, window_len, hw, C)[:, rank * fl:(rank + 1) * fl].reshape(nb * fl, hw, C)
+    return bank.reshape(nb, window_len, hw, C)[:, lo:lo + fl].reshape(nb * fl, hw, C)
 
 
 def gathered_row(j: int, b: int, px: int, nb: int, fl: int, npix: int) -> int:
-    """Row of frame j (window position), batch b, pixel px in the all-gathered [G, nb, fl, npix] K/V."""
+    """Row of frame j (window position), batch b, pixel px in the all-gathered [G, nb, fl, npix] K/V
+    (even split only: the all-gather mode needs len(window) % world == 0)."""
     g, l = divmod(j, fl)
     return ((g * nb + b) * fl + l) * npix + px
 
 
 def pixels_per_rank(hw: int, world: int) -> int:
-    """Pixels each rank owns in the pixel-sharded layout (the last rank's tail is zero padding)."""
+    """Pixels each rank owns in the pixel-sharded layout (the last rank's tail is padding)."""
     return (hw + world - 1) // world
 
 
-def frames_to_pixels(x: torch.Tensor, nb: int, fl: int, hw: int, world: int, group) -> torch.Tensor:
-    """x [(nb fl) hw, C], this rank's fl frames of every pixel  ->  [(nb F) pp, C] with F = world*fl:
-    ALL frames (window order: source rank major) of this rank's pp = ceil(hw / world) pixels.
-    Pixels >= hw (only when hw % world != 0) are zero rows.  ONE all-to-all for both CFG branches."""
+def frames_to_pixels(send: torch.Tensor, out: torch.Tensor, counts: Sequence[int], pp: int, rank: int,
+                     group) -> torch.Tensor:
+    """One CFG branch, frame-sharded -> pixel-sharded, ONE all-to-all and no layout copy on either side.
+    send [G * fl * pp, C]: this rank's fl = counts[rank] frames in the exchange layout [G(dst), fl, pp, C] that
+         mdk_groupnorm_f16 (`chunks=(G, pp)`) writes directly: block d holds pixels [d*pp, (d+1)*pp) of every frame;
+    out  [F * pp, C], F = sum(counts): ALL frames (window order) of this rank's pp pixels — rank s's block
+         [counts[s], pp, C] lands at frame offset sum(counts[:s]), so the result is frame-major as it is."""
     import torch.distributed as dist
-    C = x.shape[-1]
-    pp = pixels_per_rank(hw, world)
-    xv = x.view(nb, fl, hw, C)
-    if pp * world != hw:
-        pad = torch.zeros((nb, fl, pp * world - hw, C), dtype=x.dtype, device=x.device)
-        xv = torch.cat([xv, pad], dim=2)
-    send = xv.view(nb, fl, world, pp, C).permute(2, 0, 1, 3, 4).contiguous()   # [G(dst), nb, fl, pp, C]
-    recv = torch.empty_like(send)                                              # [G(src), nb, fl, pp, C]
-    dist.all_to_all_single(recv, send, group=group)
-    return recv.permute(1, 0, 2, 3, 4).reshape(nb * world * fl * pp, C)        # [nb, G(src), fl, pp, C]
+    world = len(counts)
+    fl = counts[rank]
+    dist.all_to_all_single(out, send, output_split_sizes=[c * pp for c in counts],
+                           input_split_sizes=[fl * pp] * world, group=group)
+    return out
 
 
-def pixels_to_frames(h: torch.Tensor, nb: int, fl: int, hw: int, world: int, group) -> torch.Tensor:
-    """Inverse of frames_to_pixels: h [(nb F) pp, C] -> [(nb fl) hw, C]."""
+def pixels_to_frames(h: torch.Tensor, back: torch.Tensor, counts: Sequence[int], pp: int, rank: int,
+                     group) -> torch.Tensor:
+    """Inverse exchange of one CFG branch: h [F * pp, C] (all frames of this rank's pixels, frame-major: the rows
+    of rank d's frames are contiguous) -> back [G(chunk), fl, pp, C] (this rank's frames, one block per pixel
+    chunk); `ops.unshard` puts the chunks back side by side."""
     import torch.distributed as dist
-    C = h.shape[-1]
-    pp = pixels_per_rank(hw, world)
-    send = h.view(nb, world, fl, pp, C).permute(1, 0, 2, 3, 4).contiguous()    # [G(dst frames), nb, fl, pp, C]
-    back = torch.empty_like(send)                                              # [G(pixel chunk), nb, fl, pp, C]
-    dist.all_to_all_single(back, send, group=group)
-    out = back.permute(1, 2, 0, 3, 4).reshape(nb, fl, world * pp, C)
-    if pp * world != hw:
-        out = out[:, :, :hw]
-    return out.reshape(nb * fl * hw, C)
+    world = len(counts)
+    fl = counts[rank]
+    dist.all_to_all_single(back, h, output_split_sizes=[fl * pp] * world,
+                           input_split_sizes=[c * pp for c in counts], group=group)
+    return back

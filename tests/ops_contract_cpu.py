@@ -120,13 +120,32 @@ def temporal_attention(qkv, *, nb, f_q, npix, heads, d, pe_q=None, kv=None, f_kv
     return O
 
 
-def groupnorm(x0, gamma, beta, *, nimg, hw, groups, eps, silu, x1=None, out=None, ws=None):
+def groupnorm(x0, gamma, beta, *, nimg, hw, groups, eps, silu, x1=None, out=None, ws=None, chunks=None):
     x = x0.double() if x1 is None else torch.cat([x0.double(), x1.double()], 1)
     C = x.shape[1]
     y = F.group_norm(x.view(nimg, hw, C).permute(0, 2, 1), groups, gamma.double(), beta.double(), eps)
     if silu:
         y = F.silu(y)
-    return _h(y.permute(0, 2, 1).reshape(nimg * hw, C))
+    y = _h(y.permute(0, 2, 1).reshape(nimg, hw, C))
+    if chunks is None:
+        return y.reshape(nimg * hw, C)
+    G, pp = chunks                                   # exchange layout [G, nimg, pp, C], padding rows zero
+    o = torch.zeros((nimg, G * pp, C), dtype=F16)
+    o[:, :hw] = y
+    return o.view(nimg, G, pp, C).permute(1, 0, 2, 3).reshape(G * nimg * pp, C).contiguous()
+
+
+def unshard(back, *, nimg, hw, chunk_pix, x=None, out=None):
+    C = back.shape[1]
+    G = back.shape[0] // (nimg * chunk_pix)
+    y = back.view(G, nimg, chunk_pix, C).permute(1, 0, 2, 3).reshape(nimg, G * chunk_pix, C)[:, :hw]
+    y = y.reshape(nimg * hw, C)
+    if x is not None:
+        y = _h(y.double() + x.double())
+    if out is None:
+        return y.contiguous()
+    out.copy_(y)
+    return out
 
 
 def layernorm(x, gamma, beta, *, eps=1e-5, add=None, add_row0=0, out=None, out2=None):
@@ -246,7 +265,7 @@ def man_modulate(x, gb, *, nimg, hw, eps=1e-5):
 
 _NAMES = ["gemm", "attention", "temporal_attention", "groupnorm", "layernorm", "upsample2x", "im2col3x3",
           "time_embed", "latents_to_nhwc", "cond_to_nhwc", "relu_", "man_modulate", "pred_accumulate",
-          "cfg_ddim_step", "quick_gelu_", "softmax_rows_", "im2col3x3_ex"]
+          "cfg_ddim_step", "quick_gelu_", "softmax_rows_", "im2col3x3_ex", "unshard"]
 
 
 def install(monkeypatch):

@@ -33,7 +33,14 @@ def test_reference_arm_prints_the_contract_line():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True
-    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the reference's own modules where /root/reference is mounted (this container), the oracle port elsewhere
+    want_kind = "reference" if os.path.isdir("/root/reference/src/models") else "port"
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == want_kind and line["cpu_baseline"]["cores"] >= 1
+    # what ran is what is reported: one frame (2 images) at the config's own latent size per timed step, and
+    # ms_per_step is its measured time (the clip extrapolation lives under cpu_baseline.extrapolated only)
+    assert line["config"]["latent"] == 32 and "latent 32x32" in line["cpu_baseline"]["sample"]
+    assert abs(line["value"] - 1.0 / (line["config"]["num_inference_steps"] * line["ms_per_step"] / 1e3)) < 1e-9
+    assert line["cpu_baseline"]["extrapolated"]["clip_s"] > 0
     assert line["e2e"] == dict(value=line["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert line["config"]["workload"].startswith("config A") and line["n_gpus"] == 1
     # under torchrun only rank 0 works: the other ranks exit 0 without output

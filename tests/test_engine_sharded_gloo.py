@@ -67,7 +67,7 @@ def _worker(rank, world, port, q, mode, h, w, F_):
 
 
 @pytest.mark.parametrize("world,mode,h,w,F_", [(2, "a2a", 8, 8, 4), (2, "allgather", 8, 8, 4),
-                                                (4, "a2a", 16, 8, 4)])
+                                                (4, "a2a", 16, 8, 4), (2, "a2a", 8, 8, 5), (4, "a2a", 8, 8, 6)])
 def test_sharded_engine_equals_single_process(world, mode, h, w, F_):
     port = 33500 + (os.getpid() % 2000) + world
     ctx = mp.get_context("spawn")

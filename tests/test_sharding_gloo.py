@@ -88,36 +88,46 @@ def test_frame_sharding_world2_gloo():
         assert ok_bank and ok_acc
 
 
-def test_uneven_window_is_rejected():
-    from mikudance_b200.sharding import shard_window
-    with pytest.raises(ValueError):
-        shard_window(list(range(30)), 0, 4)
+def test_uneven_window_split():
+    """the pipeline's default 30-frame windows over 4 / 8 GPUs (8 + 8 + 7 + 7, 6 x 4 + 2 x 3)."""
+    from mikudance_b200.sharding import frame_split, shard_window
+    assert frame_split(30, 4) == [8, 8, 7, 7] and frame_split(30, 8) == [4, 4, 4, 4, 4, 4, 3, 3]
+    assert shard_window(list(range(30)), 2, 4) == (list(range(16, 23)), 16)
     assert shard_window(list(range(32)), 3, 4) == (list(range(24, 32)), 24)
+    with pytest.raises(ValueError):
+        shard_window(list(range(3)), 0, 4)          # fewer frames than ranks
 
 
 def _worker_a2a(rank, world, port, q):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from mikudance_b200.sharding import frames_to_pixels, pixels_per_rank, pixels_to_frames
+        import ops_contract_cpu as K
+        from mikudance_b200.sharding import frame_split, frames_to_pixels, pixels_per_rank, pixels_to_frames
         res = []
-        for hw in (6, 5, 1):                      # divisible, ragged, fewer pixels than ranks
-            nb, fl, C = 2, 3, 4
-            F_ = world * fl
-            # value encodes (b, frame, pixel, channel) so any misplaced row is visible
-            full = torch.arange(nb * F_ * hw * C, dtype=torch.float32).reshape(nb, F_, hw, C) + 1.0
-            mine = full[:, rank * fl:(rank + 1) * fl].reshape(nb * fl * hw, C).contiguous()
+        for hw, F_ in ((6, 3 * world), (5, 3 * world + 1), (1, 2 * world + world - 1)):   # even / uneven frame splits
+            C = 8
+            counts = frame_split(F_, world)
+            lo, fl = sum(counts[:rank]), counts[rank]
+            # value encodes (frame, pixel, channel) so any misplaced row is visible
+            full = (torch.arange(F_ * hw * C, dtype=torch.float32).reshape(F_, hw, C) % 2000.0 + 1.0).half()
+            mine = full[lo:lo + fl].reshape(fl * hw, C).contiguous()
             pp = pixels_per_rank(hw, world)
-            got = frames_to_pixels(mine, nb, fl, hw, world, None).reshape(nb, F_, pp, C)
-            want = torch.zeros(nb, F_, pp, C)
-            lo, hi = rank * pp, min((rank + 1) * pp, hw)
-            if hi > lo:
-                want[:, :, :hi - lo] = full[:, :, lo:hi]
-            ok_fwd = torch.equal(got, want)
-            back = pixels_to_frames(got.reshape(-1, C).contiguous(), nb, fl, hw, world, None)
-            ok_rt = torch.equal(back, mine)
+            # the send buffer exactly as the GroupNorm kernel lays it out (identity affine, checked separately):
+            send = torch.zeros(fl, world * pp, C, dtype=torch.float16)
+            send[:, :hw] = mine.view(fl, hw, C)
+            send = send.view(fl, world, pp, C).permute(1, 0, 2, 3).reshape(world * fl * pp, C).contiguous()
+            got = frames_to_pixels(send, torch.empty(F_ * pp, C, dtype=torch.float16), counts, pp, rank, None)
+            want = torch.zeros(F_, pp, C, dtype=torch.float16)
+            plo, phi = rank * pp, min((rank + 1) * pp, hw)
+            if phi > plo:
+                want[:, :phi - plo] = full[:, plo:phi]
+            ok_fwd = torch.equal(got.view(F_, pp, C), want)
+            back = pixels_to_frames(got, torch.empty(world * fl * pp, C, dtype=torch.float16), counts, pp, rank, None)
+            ok_rt = torch.equal(K.unshard(back, nimg=fl, hw=hw, chunk_pix=pp), mine)
             res.append((hw, ok_fwd, ok_rt))
         q.put((rank, res))
     finally:

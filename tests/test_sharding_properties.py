@@ -6,28 +6,32 @@ from hypothesis import given, settings
 from hypothesis import strategies as st
 
 from mikudance_b200.context import uniform
-from mikudance_b200.sharding import gathered_row, pixels_per_rank, plan_ranks, shard_window, slice_bank
+from mikudance_b200.sharding import (frame_split, gathered_row, pixels_per_rank, plan_ranks, shard_window,
+                                     slice_bank)
 
 
-@settings(max_examples=60, deadline=None)
-@given(world=st.sampled_from([1, 2, 4, 8]), per=st.integers(1, 5), start=st.integers(0, 40))
-def test_shards_partition_the_window(world, per, start):
-    L = world * per
+@settings(max_examples=80, deadline=None)
+@given(world=st.sampled_from([1, 2, 3, 4, 8]), extra=st.integers(0, 20), start=st.integers(0, 40))
+def test_shards_partition_the_window(world, extra, start):
+    L = world + extra                                  # any length >= world, divisible or not
     window = [(start + i) % 64 for i in range(L)]
+    counts = frame_split(L, world)
+    assert sum(counts) == L and max(counts) - min(counts) <= 1 and counts == sorted(counts, reverse=True)
     seen = []
     for r in range(world):
         mine, lo = shard_window(window, r, world)
-        assert lo == r * per and mine == window[lo:lo + per]
+        assert lo == sum(counts[:r]) and mine == window[lo:lo + counts[r]]
         seen += mine
     assert seen == window
 
 
 @settings(max_examples=40, deadline=None)
-@given(world=st.sampled_from([1, 2, 4]), per=st.integers(1, 3), nb=st.sampled_from([1, 2]), hw=st.integers(1, 5))
-def test_bank_slices_follow_the_frame_shards(world, per, nb, hw):
-    L = world * per
+@given(world=st.sampled_from([1, 2, 4]), extra=st.integers(0, 7), nb=st.sampled_from([1, 2]), hw=st.integers(1, 5))
+def test_bank_slices_follow_the_frame_shards(world, extra, nb, hw):
+    L = world + extra
+    counts = frame_split(L, world)
     bank = torch.arange(nb * L * hw * 2, dtype=torch.float32).reshape(nb * L, hw, 2)
-    parts = [slice_bank(bank, nb, L, r, world).reshape(nb, per, hw, 2) for r in range(world)]
+    parts = [slice_bank(bank, nb, L, r, world).reshape(nb, counts[r], hw, 2) for r in range(world)]
     assert torch.equal(torch.cat(parts, dim=1).reshape(nb * L, hw, 2), bank)
 
 

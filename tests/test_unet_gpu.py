@@ -1,12 +1,13 @@
 """GPU (-m gpu): the UNet3DConditionModel forward and the denoising loop on the sm_100a path against
 the fp32 CPU oracle and against the golden vectors generated from the reference's own modules.
 
-Tolerance for a whole UNet forward (about 300 fp16-stored ops deep): the north_star's "fp16 rtol
-1e-3" is the resolution of fp16 itself, which a 300-op-deep fp16 pipeline cannot hold against an
-fp32 result — the reference's own fp16 eager path (emulated by the oracle with fp16 rounding after
-every op) sits 2.4e-3 from the fp32 oracle on the same inputs.  The gate is therefore
-    rel_l2(ours, fp32 oracle) <= 1.25 * rel_l2(reference-fp16-emulation, fp32 oracle)   and <= 5e-3,
-i.e. we must be at least as close to the fp32 truth as the reference's own fp16 arithmetic."""
+Tolerance for a whole UNet forward (about 300 fp16-stored ops deep): the north_star's "fp16 rtol 1e-3" is the
+resolution of fp16 itself, which a 300-op-deep fp16 pipeline cannot hold against an fp32 result.  The yardstick
+is measured, not modelled: the SAME oracle graph executed in real torch fp16 on the GPU (fp16 weights and
+activations through ATen / cuDNN / SDPA — the arithmetic the reference itself runs with, scripts/
+inference_video.py:66-69,95) against the fp32 oracle on the same inputs, in the same test.  The gate is
+    rel_l2(ours, fp32 oracle) <= max(1.25 * rel_l2(torch-fp16 run of the oracle, fp32 oracle), 1e-3)   and <= 5e-3
+i.e. we must be as close to the fp32 truth as the reference's own fp16 execution (measured values are printed)."""
 import os
 
 import numpy as np
@@ -41,12 +42,17 @@ def _run_case(cfg, B, f, h, w, lctx, t, with_banks):
     with torch.no_grad():
         yo = O.unet3d_forward(sd32, cfg, x.half().float(), t, ctx.half().float(), banks=banks,
                               cfg_guidance=(B == 2))
-        O.set_emulate_fp16(True)
+        # the reference's arithmetic: the oracle graph in torch fp16 on the GPU
+        O.set_compute_dtype(torch.float16)
         try:
-            y16 = O.unet3d_forward(sd32, cfg, x.half().float(), t, ctx.half().float(), banks=banks,
-                                   cfg_guidance=(B == 2))
+            sd16 = {k: v.to(D.DEV, D.F16) for k, v in sd.items()}
+            b16 = {k: v.to(D.DEV, D.F16) for k, v in banks.items()} if banks is not None else None
+            y16 = O.unet3d_forward(sd16, cfg, x.to(D.DEV, D.F16), t, ctx.to(D.DEV, D.F16), banks=b16,
+                                   cfg_guidance=(B == 2)).float().cpu()
+            del sd16, b16
         finally:
-            O.set_emulate_fp16(False)
+            O.set_compute_dtype(torch.float32)
+    print(f"unet parity: ours vs fp32 oracle {_rel(y, yo):.3e}; torch-fp16 oracle vs fp32 oracle {_rel(y16, yo):.3e}")
     return y, yo, y16
 
 
@@ -70,6 +76,17 @@ def test_unet_config_a_sd15_vs_oracle():
     y, yo, y16 = _run_case(synth.SD15_CONFIG, 2, 4, 32, 32, 257, 499, True)
     floor = _rel(y16, yo)
     assert _rel(y, yo) <= max(1.25 * floor, 1e-3) and _rel(y, yo) <= 5e-3, (_rel(y, yo), floor)
+
+
+def test_unet_config_b_shape_sd15_vs_oracle():
+    """The benchmarked shape (BASELINE config B): SD-1.5-sized UNet3D, 96x96 latents (L0 self-attention over 9216
+    tokens, d = 40: the two-stream / ones-row kernel, CTA-pair convolutions at M = 36 864 per image), 257 CLIP
+    tokens, CFG and reference banks; 2 frames (4 images) so the fp32 CPU oracle finishes in well under a minute."""
+    from mikudance_b200 import synth
+    y, yo, y16 = _run_case(synth.SD15_CONFIG, 2, 2, 96, 96, 257, 499, True)
+    floor = _rel(y16, yo)
+    assert _rel(y, yo) <= max(1.25 * floor, 1e-3) and _rel(y, yo) <= 5e-3, (_rel(y, yo), floor)
+    assert (y - yo).abs().max().item() <= 5e-3 * yo.abs().max().item() + 5e-3
 
 
 def test_cfg_uncond_half_ignores_banks_on_gpu():
