@@ -179,6 +179,25 @@ def check_norms():
         if silu:
             ref = torch.nn.functional.silu(ref)
         ok &= report(f"groupnorm n={nimg} hw={hw} c={c0}+{c1}", out, ref.permute(0, 2, 1).reshape(-1, C_))
+    # exchange layout of the frame-sharded motion modules: [G, nimg, pp, C] written by the apply pass (bit-identical
+    # values, rows of pixels >= hw zero), and the way back (unshard, with and without the fused residual add)
+    for (nimg, hw, c, G) in [(3, 256, 320, 4), (2, 145, 64, 4), (4, 9, 1280, 8), (2, 1, 64, 2)]:
+        x0 = (rnd(nimg * hw, c) * 2 + 0.5).to(F16)
+        gm = (1 + 0.1 * rnd(c)).to(F16)
+        bt = (0.1 * rnd(c, seed=4)).to(F16)
+        plain = ops.groupnorm(x0, gm, bt, nimg=nimg, hw=hw, groups=32, eps=1e-6, silu=False)
+        pp = (hw + G - 1) // G
+        ex = ops.groupnorm(x0, gm, bt, nimg=nimg, hw=hw, groups=32, eps=1e-6, silu=False, chunks=(G, pp))
+        want = torch.zeros(nimg, G * pp, c, dtype=F16, device=DEV)
+        want[:, :hw] = plain.view(nimg, hw, c)
+        want = want.view(nimg, G, pp, c).permute(1, 0, 2, 3).reshape(G * nimg * pp, c)
+        e1 = torch.equal(ex, want)
+        e2 = torch.equal(ops.unshard(ex, nimg=nimg, hw=hw, chunk_pix=pp), plain)
+        res = rnd(nimg * hw, c, seed=21).to(F16)
+        e3 = torch.equal(ops.unshard(ex, nimg=nimg, hw=hw, chunk_pix=pp, x=res), (plain.float() + res.float()).half())
+        print(f"[{'OK ' if (e1 and e2 and e3) else 'FAIL'}] groupnorm exchange layout / unshard n={nimg} hw={hw} c={c} G={G}: "
+              f"layout {e1} round-trip {e2} fused add {e3}", flush=True)
+        ok &= e1 and e2 and e3
     for (rows, c) in [(1000, 320), (517, 640), (300, 1280), (64, 64)]:
         x = (rnd(rows, c) * 1.5 + 0.2).to(F16)
         gm = (1 + 0.1 * rnd(c)).to(F16)

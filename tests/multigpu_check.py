@@ -59,7 +59,7 @@ def main():
             m.engine().shard_mode = mode
             # the all-gather mode runs the gathered-layout SIMT temporal kernel; its single-GPU anchor
             # is the same kernel on one GPU (different rounding than the mma.sync tile kernel)
-            m.engine().force_simt = (name == "single-simt")
+            m.engine().force_simt = (mode == "allgather")   # (also when the CFG split leaves one rank per branch)
             loop = DenoiseLoop(m, DDIMScheduler(**kw), guidance_scale=3.5, context_frames=ctxf,
                                context_stride=1, context_overlap=ov, process_group=pg, use_cuda_graph=graph)
             loop.prepare(lat.to(dev).contiguous().clone(), ctx, 3, banks_for_window)
