@@ -504,7 +504,10 @@ def main():
                     warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="f16", data="synthetic",
                     config=config,
-                    execution=dict(parallelism=f"frames sharded over {world} GPU(s)", cuda_graph=not args.no_graph),
+                    execution=dict(parallelism=(f"{world} GPU(s): CFG branches on the two halves of the ranks, frames of "
+                                                f"each window sharded over {loop.sub_world} rank(s)" if loop.branch >= 0
+                                                else f"frames of each window sharded over {world} GPU(s)"),
+                                   frames_per_rank=[w["fl"] for w in loop.win], cuda_graph=not args.no_graph),
                     clocks=clocks,
                     e2e=dict(value=F_ / (num_steps * ms_e2e / 1e3), unit="frames/s", ms_per_step=ms_e2e,
                              h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
@@ -513,8 +516,9 @@ def main():
                                   "output) are uploaded once per clip, like the weights"),
                     gpu_launches=launches_per_step * args.steps, launches_per_step=launches_per_step,
                     roofline=dict(kernel="whole denoising step (all kernels; deduplicated algorithmic FLOPs, BASELINE.md)",
-                                  bound="tensor", achieved=step_ach, peak=peaks["tflops_sustained"], unit="TFLOP/s",
-                                  frac=(step_ach / peaks["tflops_sustained"]) if step_ach else None, traffic=None,
+                                  bound="tensor", achieved=step_ach, peak=peaks["tflops_sustained"] * world, unit="TFLOP/s",
+                                  frac=(step_ach / (peaks["tflops_sustained"] * world)) if step_ach else None, traffic=None,
+                                  peak_per_gpu=peaks["tflops_sustained"],
                                   algorithmic_tflop_per_step=step_tflop,
                                   peak_source=peaks["source"] + ", sustained bf16 GEMM"),
                     roofline_gemm=roofline,
