@@ -138,15 +138,25 @@ __global__ void gn_apply_kernel(const GnParams p) {
   const __half* src = from1 ? p.x1 : p.x0;
   const int cs = from1 ? p.c1 : p.c0;
   const int coff = from1 ? ch - p.c0 : ch;
-  // mean / rstd of every group: combined once per CTA from the per-chunk partials (fixed order, fp64)
+  // mean / rstd of every group: combined once per CTA from the per-chunk partials (fixed order, fp64).  The
+  // partials are fetched by ALL threads first (one coalesced wave of loads) and summed from shared memory: a
+  // serial loop of nchunks dependent global loads per group thread kept the whole CTA at the barrier below for
+  // ~10 us of a ~20 us lifetime.
   __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float s_part[GN_MAX_CHUNKS * 64 * 2];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  {
+    const float* part = p.ws + static_cast<long long>(img) * GN_MAX_CHUNKS * p.groups * 2;
+    const int n = p.nchunks * p.groups * 2;      // chunk-major, contiguous: [k][group][2]
+    for (int i = tid; i < n; i += nthr) s_part[i] = part[i];
+  }
+  __syncthreads();
   if (tid < p.groups) {
     double sum = 0.0, sq = 0.0;
     for (int k = 0; k < p.nchunks; ++k) {
-      const float* part = p.ws + ((static_cast<long long>(img) * GN_MAX_CHUNKS + k) * p.groups + tid) * 2;
-      sum += static_cast<double>(part[0]);
-      sq += static_cast<double>(part[1]);
+      sum += static_cast<double>(s_part[(k * p.groups + tid) * 2]);
+      sq += static_cast<double>(s_part[(k * p.groups + tid) * 2 + 1]);
     }
     const double cnt = static_cast<double>(p.hw) * p.cpg;
     const double mean = sum / cnt;

@@ -8,6 +8,8 @@
 //
 // Algorithmic bytes per launch: 2 * nb*npix*C * (2*f_q + 2*f_kv) (Q + O over f_q frames, K + V
 // over f_kv frames).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 #include "../../include/mdk.h"
@@ -202,32 +204,12 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t& r0, u
 // a 16 x 16 x 40 problem cannot fill a tcgen05 128-row tile, the kernel is HBM-bound, and
 // m16n8k16 fragments can be fed straight from the staged rows (row stride 3C+8 halves makes every
 // fragment load bank-conflict free).  MT = number of 16-row query tiles (frames padded to 16*MT).
+// The (pixel, head) problems of one staged item: warp w < hg computes head w of the group from the rows at `sm`
+// (q | k | v segments per frame row, row stride p.rs halves) and overwrites the Q slots with O.
 template <int MT>
-__global__ void __launch_bounds__(256) temporal_attn_tile_kernel(const TattnTileParams p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  __half* sm = reinterpret_cast<__half*>(smem_raw);
+__device__ __forceinline__ void tattn_compute_item(const TattnTileParams& p, __half* sm) {
   constexpr int FP = 16 * MT;
-  // CTA = (batch entry, pixel, head group): small CTAs (31 KB of smem at any level) so that 6-7 of
-  // them overlap their load / compute / store phases on one SM
-  const int ngroups = p.heads / p.hg;
-  const int hgi = blockIdx.x % ngroups;
-  const long long bp = blockIdx.x / ngroups;
-  const int px = static_cast<int>(bp % p.npix);
-  const int b = static_cast<int>(bp / p.npix);
-  const int segv = p.seg >> 3;           // 16-byte vectors per segment
-  const int col0 = hgi * p.seg;          // first channel of this head group
-  // ---- load the q | k | v segments of every frame (zero rows for padded frames) ----
-  for (int i = threadIdx.x; i < FP * 3 * segv; i += blockDim.x) {
-    const int v = i % segv;
-    const int which = (i / segv) % 3;
-    const int j = i / (3 * segv);
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (j < p.f)
-      val = *reinterpret_cast<const uint4*>(
-          p.qkv + ((static_cast<long long>(b) * p.f + j) * p.npix + px) * p.ld + which * p.C + col0 + v * 8);
-    *reinterpret_cast<uint4*>(sm + static_cast<long long>(j) * p.rs + which * p.seg + v * 8) = val;
-  }
-  __syncthreads();
+  (void)FP;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int ksteps = (p.d + 15) >> 4;
@@ -345,6 +327,35 @@ __global__ void __launch_bounds__(256) temporal_attn_tile_kernel(const TattnTile
       }
     }
   }
+}
+
+template <int MT>
+__global__ void __launch_bounds__(256) temporal_attn_tile_kernel(const TattnTileParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __half* sm = reinterpret_cast<__half*>(smem_raw);
+  constexpr int FP = 16 * MT;
+  // CTA = (batch entry, pixel, head group): small CTAs (31 KB of smem at any level) so that 6-7 of
+  // them overlap their load / compute / store phases on one SM
+  const int ngroups = p.heads / p.hg;
+  const int hgi = blockIdx.x % ngroups;
+  const long long bp = blockIdx.x / ngroups;
+  const int px = static_cast<int>(bp % p.npix);
+  const int b = static_cast<int>(bp / p.npix);
+  const int segv = p.seg >> 3;           // 16-byte vectors per segment
+  const int col0 = hgi * p.seg;          // first channel of this head group
+  // ---- load the q | k | v segments of every frame (zero rows for padded frames) ----
+  for (int i = threadIdx.x; i < FP * 3 * segv; i += blockDim.x) {
+    const int v = i % segv;
+    const int which = (i / segv) % 3;
+    const int j = i / (3 * segv);
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (j < p.f)
+      val = *reinterpret_cast<const uint4*>(
+          p.qkv + ((static_cast<long long>(b) * p.f + j) * p.npix + px) * p.ld + which * p.C + col0 + v * 8);
+    *reinterpret_cast<uint4*>(sm + static_cast<long long>(j) * p.rs + which * p.seg + v * 8) = val;
+  }
+  __syncthreads();
+  tattn_compute_item<MT>(p, sm);
   __syncthreads();
   // ---- store the O segment of every frame (first `seg` columns of every staged row) ----
   for (int i = threadIdx.x; i < p.f * segv; i += blockDim.x) {
@@ -352,6 +363,67 @@ __global__ void __launch_bounds__(256) temporal_attn_tile_kernel(const TattnTile
     *reinterpret_cast<uint4*>(p.out + ((static_cast<long long>(b) * p.f + j) * p.npix + px) * p.out_ld +
                               col0 + v * 8) =
         *reinterpret_cast<const uint4*>(sm + static_cast<long long>(j) * p.rs + v * 8);
+  }
+}
+
+// Pipelined variant (default): a CTA walks a strided list of (batch entry, pixel, head group) items with TWO
+// staging buffers — the 16-byte cp.async loads of item i+1 are in flight while item i is computed and stored — so
+// every resident CTA always has ~30 KB of loads outstanding (the one-item-per-CTA kernel above alternates
+// load / compute / store phases and measured 2.3 TB/s of the 6.5 TB/s copy bandwidth).  Rows of padded frames
+// (f < 16 MT) are zeroed once; loads never touch them (only their dead Q slots are overwritten by O).
+template <int MT>
+__global__ void __launch_bounds__(256) temporal_attn_pipe_kernel(const TattnTileParams p, long long nitems) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int FP = 16 * MT;
+  const int stage_halves = FP * p.rs;
+  __half* st0 = reinterpret_cast<__half*>(smem_raw);
+  const int ngroups = p.heads / p.hg;
+  const int segv = p.seg >> 3;
+  for (int i = threadIdx.x; i < 2 * stage_halves / 8; i += blockDim.x)
+    reinterpret_cast<uint4*>(st0)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  auto issue_loads = [&](long long item, __half* sm) {
+    const int hgi = static_cast<int>(item % ngroups);
+    const long long bp = item / ngroups;
+    const int px = static_cast<int>(bp % p.npix);
+    const int b = static_cast<int>(bp / p.npix);
+    const int col0 = hgi * p.seg;
+    for (int i = threadIdx.x; i < p.f * 3 * segv; i += blockDim.x) {
+      const int v = i % segv;
+      const int which = (i / segv) % 3;
+      const int j = i / (3 * segv);
+      const __half* src = p.qkv + ((static_cast<long long>(b) * p.f + j) * p.npix + px) * p.ld + which * p.C + col0 + v * 8;
+      const uint32_t dst = smem_u32(sm + static_cast<long long>(j) * p.rs + which * p.seg + v * 8);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  long long item = blockIdx.x;
+  if (item < nitems) issue_loads(item, st0);
+  int s = 0;
+  for (; item < nitems; item += gridDim.x, s ^= 1) {
+    __half* sm = st0 + static_cast<long long>(s) * stage_halves;
+    const long long next = item + gridDim.x;
+    if (next < nitems) {
+      issue_loads(next, st0 + static_cast<long long>(s ^ 1) * stage_halves);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncthreads();
+    tattn_compute_item<MT>(p, sm);
+    __syncthreads();
+    const int hgi = static_cast<int>(item % ngroups);
+    const long long bp = item / ngroups;
+    const int px = static_cast<int>(bp % p.npix);
+    const int b = static_cast<int>(bp / p.npix);
+    const int col0 = hgi * p.seg;
+    for (int i = threadIdx.x; i < p.f * segv; i += blockDim.x) {
+      const int v = i % segv, j = i / segv;
+      *reinterpret_cast<uint4*>(p.out + ((static_cast<long long>(b) * p.f + j) * p.npix + px) * p.out_ld + col0 + v * 8) =
+          *reinterpret_cast<const uint4*>(sm + static_cast<long long>(j) * p.rs + v * 8);
+    }
+    __syncthreads();   // the buffer is free for the loads of item i+2
   }
 }
 
@@ -413,10 +485,30 @@ extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void
       const long long grid = static_cast<long long>(a->nb) * a->npix * (a->heads / hg);
       MDK_REQUIRE(grid < (1ll << 31), "mdk_temporal_attn_f16: grid too large");
       const int threads = 32 * hg < 64 ? 64 : 32 * hg;
-      if (a->f_q <= 16)
+      static int pipe = -1;
+      if (pipe < 0) {
+        const char* e = getenv("MDK_TATTN_PIPE");
+        pipe = e ? atoi(e) : 1;
+      }
+      if (pipe && 2 * smem <= 200 * 1024) {
+        MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_pipe_kernel<1>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_pipe_kernel<2>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int per_sm = static_cast<int>((220 * 1024) / (2 * smem + 1024));
+        if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+        if (per_sm < 1) per_sm = 1;
+        long long ctas = static_cast<long long>(ctx->num_sms) * per_sm;
+        if (ctas > grid) ctas = grid;
+        if (a->f_q <= 16)
+          temporal_attn_pipe_kernel<1><<<static_cast<unsigned>(ctas), threads, 2 * smem, stream>>>(t, grid);
+        else
+          temporal_attn_pipe_kernel<2><<<static_cast<unsigned>(ctas), threads, 2 * smem, stream>>>(t, grid);
+      } else if (a->f_q <= 16) {
         temporal_attn_tile_kernel<1><<<static_cast<unsigned>(grid), threads, smem, stream>>>(t);
-      else
+      } else {
         temporal_attn_tile_kernel<2><<<static_cast<unsigned>(grid), threads, smem, stream>>>(t);
+      }
       count_launch();
       MDK_CHECK_CUDA(cudaGetLastError());
       return 0;

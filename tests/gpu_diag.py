@@ -103,6 +103,13 @@ def check_gemm_epilogue():
         idx += list(range(t * 128, t * 128 + 128)) + list(range(Nn // 2 + t * 128, Nn // 2 + t * 128 + 128))
     idx = torch.tensor(idx, device=DEV)
     ok &= report("geglu", ops.gemm(a, wg[idx].contiguous(), bias=bg[idx].contiguous(), geglu=True), refg)
+    # gates far in the tails (|g| up to ~25): the erf GELU is evaluated as x * sigmoid(2 x poly(x^2)) with x clamped
+    # inside the polynomial only
+    full6 = (a.float() * 6.0) @ wg.float().t() + bg
+    ok &= report("geglu (gate gain 6)", ops.gemm((a.float() * 6.0).to(F16), wg[idx].contiguous(), bias=bg[idx].contiguous(),
+                                                 geglu=True),
+                 ((a.float() * 6.0).to(F16).float() @ wg.float().t() + bg)[:, :Nn // 2]
+                 * torch.nn.functional.gelu(((a.float() * 6.0).to(F16).float() @ wg.float().t() + bg)[:, Nn // 2:]))
     # segments + transposed V
     nimg, L = 3, 259
     M2 = nimg * L
@@ -882,7 +889,7 @@ def ab_attn_switches():
     extra = ({"MDK_ATTN_SPLITKV": "1"}, {"MDK_ATTN_SPLITKV": "1", "MDK_ATTN_POLY": "1"},
              {"MDK_ATTN_2S": "1"}, {"MDK_ATTN_2S": "1", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_2S": "1", "MDK_ATTN_POLY": "2"},
              {"MDK_ATTN_2S": "2"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "2"})
-    for env in ({}, {"MDK_ATTN_POLY": "1"}, {"MDK_ATTN_STALE": "1", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_SK": "1"},
+    for env in ({}, {"MDK_ATTN_2S": "0"}, {"MDK_ATTN_2S": "0", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_STALE": "1", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_SK": "1"},
                 {"MDK_ATTN_PP": "3"}, {"MDK_ATTN_BKV": "64"}) + extra + ({},):
         for n in names:
             os.environ.pop(n, None)

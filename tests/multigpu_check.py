@@ -50,7 +50,10 @@ def main():
             return synth.synthetic_banks(cfg, 2 * len(wdw), h, w, seed=300 + wdw[0])
 
         res = {}
-        uneven = F_ % world != 0 or (os.environ.get("MDK_CFG_SPLIT", "1") == "1" and world % 2 == 0 and F_ % (world // 2) != 0)
+        from mikudance_b200.context import get_context_scheduler
+        from mikudance_b200.sharding import plan_ranks
+        sub_world = plan_ranks(rank, world, True, os.environ.get("MDK_CFG_SPLIT", "1") == "1")["sub_world"]
+        uneven = any(len(x) % sub_world for x in get_context_scheduler("uniform")(0, 3, F_, ctxf, 1, ov))
         cases = [("single", None, True, "a2a"), ("sharded", dist.group.WORLD, True, "a2a"),
                  ("sharded-eager", dist.group.WORLD, False, "a2a")]
         if not uneven:

@@ -57,7 +57,7 @@ def test_flash_attention_tcgen05():
     assert D.check_attn()
 
 
-@pytest.mark.parametrize("env", [{"MDK_ATTN_SK": "1"}, {"MDK_ATTN_PP": "3"}, {"MDK_ATTN_PP": "0"},
+@pytest.mark.parametrize("env", [{"MDK_ATTN_2S": "0"}, {"MDK_ATTN_2S": "0", "MDK_ATTN_SK": "1"}, {"MDK_ATTN_PP": "3"}, {"MDK_ATTN_PP": "0"},
                                  {"MDK_ATTN_BKV": "64"}, {"MDK_ATTN_BKV": "128", "MDK_ATTN_PP": "0"},
                                  {"MDK_ATTN_POLY": "1"}, {"MDK_ATTN_STALE": "1"},
                                  {"MDK_ATTN_2S": "1"}, {"MDK_ATTN_2S": "1", "MDK_ATTN_POLY": "1"},
