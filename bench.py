@@ -324,6 +324,9 @@ def main():
     ap.add_argument("--skip-profile", action="store_true")
     ap.add_argument("--skip-reference-unet", action="store_true",
                     help="do not time the hoisted reference UNet (writer) forward that produces the banks")
+    ap.add_argument("--frames", type=int, default=0,
+                    help="experiments only: override the clip's frame count (e.g. 2 = the per-rank workload of "
+                         "config B on 8 GPUs); the line's config states the frames actually run")
     ap.add_argument("--ncu-step", action="store_true",
                     help="run ONE eager step inside a cudaProfilerStart/Stop range and exit "
                          "(for `ncu --profile-from-start off`; prints no bench line)")
@@ -331,6 +334,8 @@ def main():
     if args.ncu_step:
         args.no_graph = True
     h, F_, num_steps, ctx_frames = CONFIGS[args.config]
+    if args.frames > 0:
+        F_ = args.frames
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     workload = dict(workload=f"config {args.config}: {h * 8}x{h * 8}, {F_} frames, {num_steps} DDIM steps, CFG 3.5, "

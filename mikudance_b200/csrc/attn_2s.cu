@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(A2S_THREADS, 2) attn_2s_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_trigger();
 
   // Register reallocation, warpgroup-uniform and issued INSIDE each role's branch (ptxas budgets a region by
   // the setmaxnreg that dominates it): the driver warpgroup keeps 40 registers per thread, the two softmax
@@ -452,9 +454,8 @@ static int launch_attn_2s_t(AttnParams& p, const mdk_attn_args* a, cudaStream_t 
   if (encode_attn_maps(p, a, A2S_BKV)) return -1;
   p.n_kv_tiles = (a->lkv + A2S_BKV - 1) / A2S_BKV;
   dim3 grid((a->lq + ATT_BQ - 1) / ATT_BQ, a->heads, a->nimg);
-  attn_2s_kernel<ONES, POLY, SELF, TRACE><<<grid, A2S_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  MDK_CHECK_CUDA(launch_pdl(attn_2s_kernel<ONES, POLY, SELF, TRACE>, grid, dim3(A2S_THREADS), Cfg::SMEM_BYTES, stream, p));
   count_launch();
-  MDK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

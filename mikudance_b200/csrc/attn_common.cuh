@@ -82,4 +82,7 @@ inline int encode_attn_maps(AttnParams& p, const mdk_attn_args* a, int bkv) {
 int launch_attn_2s(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a, cudaStream_t stream, int variant,
                    long long* trace, int trace_cap);
 
+// attn_2s32.cu: the two-stream kernel with 32-key sub-tiles (S half-tiles as a double buffer)
+int launch_attn_2s32(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a, cudaStream_t stream);
+
 }  // namespace mdk

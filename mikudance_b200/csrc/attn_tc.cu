@@ -134,6 +134,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -496,9 +498,9 @@ static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a
   if (encode_attn_maps(p, a, BKV)) return -1;
   p.n_kv_tiles = (a->lkv + BKV - 1) / BKV;
   dim3 grid((a->lq + ATT_BQ - 1) / ATT_BQ, a->heads, a->nimg);
-  attn_tc_kernel<NCH, BKV, KST, ONES, SPLIT, TRACE><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  MDK_CHECK_CUDA(launch_pdl(attn_tc_kernel<NCH, BKV, KST, ONES, SPLIT, TRACE>, grid, dim3(ATT_THREADS), Cfg::SMEM_BYTES,
+                            stream, p));
   count_launch();
-  MDK_CHECK_CUDA(cudaGetLastError());
   (void)ctx;
   return 0;
 }
@@ -592,6 +594,8 @@ attn_pp_kernel(const __grid_constant__ AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -863,9 +867,8 @@ static int launch_attn_pp(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args
   if (encode_attn_maps(p, a, BKV)) return -1;
   p.n_kv_tiles = (a->lkv + BKV - 1) / BKV;
   dim3 grid((a->lq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), a->heads, a->nimg);
-  attn_pp_kernel<NCH, BKV, KST, ONES><<<grid, ATT_PP_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  MDK_CHECK_CUDA(launch_pdl(attn_pp_kernel<NCH, BKV, KST, ONES>, grid, dim3(ATT_PP_THREADS), Cfg::SMEM_BYTES, stream, p));
   count_launch();
-  MDK_CHECK_CUDA(cudaGetLastError());
   (void)ctx;
   return 0;
 }
@@ -943,6 +946,8 @@ attn_sk_kernel(const __grid_constant__ AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -1212,9 +1217,8 @@ static int launch_attn_sk(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args
   if (encode_attn_maps(p, a, SK_BKV)) return -1;
   p.n_kv_tiles = (a->lkv + SK_BKV - 1) / SK_BKV;
   dim3 grid((a->lq + ATT_BQ - 1) / ATT_BQ, a->heads, a->nimg);
-  attn_sk_kernel<KST, ONES><<<grid, ATT_SK_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  MDK_CHECK_CUDA(launch_pdl(attn_sk_kernel<KST, ONES>, grid, dim3(ATT_SK_THREADS), Cfg::SMEM_BYTES, stream, p));
   count_launch();
-  MDK_CHECK_CUDA(cudaGetLastError());
   (void)ctx;
   return 0;
 }
@@ -1285,6 +1289,7 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
     const int two = e ? atoi(e) : ((a->vt_ones && a->lkv >= 1024 && a->lq >= 256) ? 1 : 0);
     if (two) {
       if (!getenv("MDK_ATTN_POLY") && a->vt_ones) p.poly = 1;
+      if (two == 3) return launch_attn_2s32(ctx, p, a, stream);   // 32-key sub-tiles (attn_2s32.cu)
       const char* etr = getenv("MDK_ATTN_TRACE");
       const bool trace = etr && atoi(etr) && g_attn_trace != nullptr;
       return launch_attn_2s(ctx, p, a, stream, two, trace ? g_attn_trace : nullptr, g_attn_trace_cap);

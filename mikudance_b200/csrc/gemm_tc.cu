@@ -225,6 +225,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();      // everything above touched no global memory: it overlaps the previous kernel's tail
+  pdl_trigger();
 
   const int total_tiles = p.mp_tiles * p.n_tiles;   // tiles per CTA (pair tiles for CG == 2)
   const int kblocks_per_tap = p.kb0 + p.kb1;
@@ -714,21 +716,22 @@ static int launch_gemm(const mdk_ctx* ctx, const GemmParams& p, cudaStream_t str
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MDK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, p));
     count_launch();
     return 0;
   }
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  gemm_tc_kernel<BN, CG><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  MDK_CHECK_CUDA(launch_pdl(gemm_tc_kernel<BN, CG>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p));
   count_launch();
-  MDK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

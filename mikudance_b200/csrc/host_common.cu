@@ -75,6 +75,15 @@ int encode_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t
   return 0;
 }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MDK_PDL");
+    on = e ? (atoi(e) != 0) : 1;
+  }
+  return on != 0;
+}
+
 }  // namespace mdk
 
 extern "C" {

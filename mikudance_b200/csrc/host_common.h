@@ -8,6 +8,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <utility>
 
 struct mdk_ctx {
   int device;
@@ -33,6 +34,32 @@ inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relax
   do {                                               \
     if (!(cond)) return mdk::set_error(__VA_ARGS__); \
   } while (0)
+
+// Programmatic dependent launch (PDL): the kernels of the denoising step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, execute `griddepcontrol.wait` before their first global
+// memory access and `griddepcontrol.launch_dependents` right after it (ptx.cuh: pdl_wait / pdl_trigger).  The next
+// kernel of the stream is then scheduled while this one still runs — its launch latency and prologue (barrier
+// init, TMEM allocation, tensor-map prefetch, smem zeroing) overlap the tail of its predecessor — and blocks in
+// hardware at its own wait until the predecessor has completed and flushed.  A step is ~750 launches of 20-400 us
+// kernels (22 ms per step on 8 GPUs): the 2-3 us between dependent kernels is what PDL removes.  Captured by CUDA
+// graphs as programmatic edges.  MDK_PDL=0 launches everything fully serialised.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Encode a tiled fp16 tensor map (rank 2..5). dims/strides innermost first; strides in BYTES for
 // dims 1..rank-1 (dim 0 is dense). 128-byte swizzle, zero fill out of bounds.

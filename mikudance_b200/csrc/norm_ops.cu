@@ -56,6 +56,8 @@ __device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
 // fixed-order reduction over the channels of each group -> one partial per (image, chunk, group).
 __global__ void gn_stats_kernel(const GnParams p) {
   extern __shared__ float s_red[];  // [vy][vx][16] then col[2][C]
+  pdl_wait();
+  pdl_trigger();
   const int img = blockIdx.y;
   const int cv = threadIdx.x;
   const int V = p.C >> 3;
@@ -130,6 +132,8 @@ __global__ void gn_stats_kernel(const GnParams p) {
 }
 
 __global__ void gn_apply_kernel(const GnParams p) {
+  pdl_wait();
+  pdl_trigger();
   const int img = blockIdx.y;
   const int cv = threadIdx.x;
   const int V = p.C >> 3;
@@ -241,6 +245,8 @@ struct LnParams {
 // per lane: the kernel is latency-bound otherwise).
 template <int NV, int R>
 __global__ void layernorm_kernel(const LnParams p) {
+  pdl_wait();
+  pdl_trigger();
   const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int V = p.c >> 3;
@@ -333,6 +339,8 @@ __global__ void layernorm_kernel(const LnParams p) {
 // lane slots: 62 % / 83 % of the lanes busy).  RR rows per group in flight.
 template <int LPR, int RR>
 __global__ void layernorm_lpr_kernel(const LnParams p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int GPW = 32 / LPR;  // row groups per warp
   const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -422,7 +430,7 @@ static void launch_ln_lpr(const LnParams& p, int num_sms, cudaStream_t stream) {
   long long ctas = (groups + warps - 1) / warps;
   const long long cap = static_cast<long long>(num_sms) * 8;
   if (ctas > cap) ctas = cap;
-  layernorm_lpr_kernel<LPR, RR><<<static_cast<unsigned>(ctas), warps * 32, 0, stream>>>(p);
+  launch_pdl(layernorm_lpr_kernel<LPR, RR>, dim3(static_cast<unsigned>(ctas)), dim3(warps * 32), 0, stream, p);
 }
 
 template <int NV, int R>
@@ -432,7 +440,7 @@ static void launch_ln(const LnParams& p, int num_sms, cudaStream_t stream) {
   long long ctas = (groups + warps - 1) / warps;
   const long long cap = static_cast<long long>(num_sms) * 8;
   if (ctas > cap) ctas = cap;
-  layernorm_kernel<NV, R><<<static_cast<unsigned>(ctas), warps * 32, 0, stream>>>(p);
+  launch_pdl(layernorm_kernel<NV, R>, dim3(static_cast<unsigned>(ctas)), dim3(warps * 32), 0, stream, p);
 }
 
 }  // namespace mdk
@@ -529,9 +537,9 @@ extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* strea
     q.nchunks = chunks;
     dim3 block(vx, vy);
     dim3 grid(chunks, ni);
-    gn_stats_kernel<<<grid, block, stats_smem, stream>>>(q);
+    MDK_CHECK_CUDA(launch_pdl(gn_stats_kernel, grid, block, stats_smem, stream, q));
     count_launch();
-    gn_apply_kernel<<<grid, block, 0, stream>>>(q);
+    MDK_CHECK_CUDA(launch_pdl(gn_apply_kernel, grid, block, 0, stream, q));
     count_launch();
   }
   MDK_CHECK_CUDA(cudaGetLastError());

@@ -13,6 +13,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Programmatic dependent launch (host_common.h): wait until the preceding kernel of the stream has completed and
+// its writes are visible (no-op when launched without the attribute), then let the next kernel be scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 __device__ __forceinline__ bool elect_one() {

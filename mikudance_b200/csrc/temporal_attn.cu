@@ -382,6 +382,8 @@ __global__ void __launch_bounds__(256) temporal_attn_pipe_kernel(const TattnTile
   for (int i = threadIdx.x; i < 2 * stage_halves / 8; i += blockDim.x)
     reinterpret_cast<uint4*>(st0)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
   auto issue_loads = [&](long long item, __half* sm) {
     const int hgi = static_cast<int>(item % ngroups);
     const long long bp = item / ngroups;
@@ -501,9 +503,11 @@ extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void
         long long ctas = static_cast<long long>(ctx->num_sms) * per_sm;
         if (ctas > grid) ctas = grid;
         if (a->f_q <= 16)
-          temporal_attn_pipe_kernel<1><<<static_cast<unsigned>(ctas), threads, 2 * smem, stream>>>(t, grid);
+          MDK_CHECK_CUDA(launch_pdl(temporal_attn_pipe_kernel<1>, dim3(static_cast<unsigned>(ctas)), dim3(threads), 2 * smem,
+                                    stream, t, grid));
         else
-          temporal_attn_pipe_kernel<2><<<static_cast<unsigned>(ctas), threads, 2 * smem, stream>>>(t, grid);
+          MDK_CHECK_CUDA(launch_pdl(temporal_attn_pipe_kernel<2>, dim3(static_cast<unsigned>(ctas)), dim3(threads), 2 * smem,
+                                    stream, t, grid));
       } else if (a->f_q <= 16) {
         temporal_attn_tile_kernel<1><<<static_cast<unsigned>(grid), threads, smem, stream>>>(t);
       } else {

@@ -888,7 +888,8 @@ def ab_attn_switches():
              "MDK_ATTN_2S")
     extra = ({"MDK_ATTN_SPLITKV": "1"}, {"MDK_ATTN_SPLITKV": "1", "MDK_ATTN_POLY": "1"},
              {"MDK_ATTN_2S": "1"}, {"MDK_ATTN_2S": "1", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_2S": "1", "MDK_ATTN_POLY": "2"},
-             {"MDK_ATTN_2S": "2"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "2"})
+             {"MDK_ATTN_2S": "2"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "2"},
+             {"MDK_ATTN_2S": "3", "MDK_ATTN_POLY": "0"}, {"MDK_ATTN_2S": "3"}, {"MDK_ATTN_2S": "3", "MDK_ATTN_POLY": "2"})
     for env in ({}, {"MDK_ATTN_2S": "0"}, {"MDK_ATTN_2S": "0", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_STALE": "1", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_SK": "1"},
                 {"MDK_ATTN_PP": "3"}, {"MDK_ATTN_BKV": "64"}) + extra + ({},):
         for n in names:

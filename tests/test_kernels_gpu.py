@@ -62,6 +62,7 @@ def test_flash_attention_tcgen05():
                                  {"MDK_ATTN_POLY": "1"}, {"MDK_ATTN_STALE": "1"},
                                  {"MDK_ATTN_2S": "1"}, {"MDK_ATTN_2S": "1", "MDK_ATTN_POLY": "1"},
                                  {"MDK_ATTN_2S": "2"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "2"},
+                                 {"MDK_ATTN_2S": "3"}, {"MDK_ATTN_2S": "3", "MDK_ATTN_POLY": "0"},
                                  {"MDK_ATTN_SPLITKV": "1"}, {"MDK_ATTN_SPLITKV": "1", "MDK_ATTN_POLY": "1"}])
 def test_flash_attention_alternative_kernels(monkeypatch, env):
     """The kernels the dispatch heuristics do not pick by default (split-key, ping-pong for every
