@@ -126,6 +126,15 @@ class MikuDanceVideoPipeline:
                  context_batch_size=1, interpolation_factor=1, latents=None, **kwargs):
         if eta != 0.0:
             raise NotImplementedError("eta > 0 is not used by the reference's DDIM configuration")
+        if self.video_decoder:
+            # the reference decodes with AutoencoderKLTemporalDecoder.decode(num_frames=) in chunks of 16
+            # (pipeline_mikudance.py:132-150, 692-695); that model is outside the hot path and not provided:
+            # never fall back silently to the per-frame decoder
+            raise NotImplementedError("video_decoder=True (temporal VAE decoder) is not implemented; "
+                                      "construct the pipeline with video_decoder=False")
+        if num_images_per_prompt != 1:
+            raise NotImplementedError("num_images_per_prompt != 1: the denoising loop works on a latent batch of 1 "
+                                      "(as scripts/inference_video.py calls it)")
         if context_batch_size != 1:
             raise NotImplementedError("context_batch_size != 1 (the reference always uses 1)")
         if interpolation_factor >= 2:
@@ -203,7 +212,7 @@ class MikuDanceVideoPipeline:
                     callback(i, t, lat)
             latents = loop.run(callback=cb, callback_steps=1).to(dtype)
 
-        images = self.decode_latents(latents) if not self.video_decoder else self.decode_latents(latents)
+        images = self.decode_latents(latents)
         if output_type == "tensor":
             images = torch.from_numpy(images)
         if not return_dict:

@@ -1,5 +1,6 @@
 """GPU (-m gpu): the native VAE against the fp32 restatement of diffusers' AutoencoderKL
-(oracle/vae_oracle.py — diffusers is absent here, so that restatement is itself unpinned).
+(oracle/vae_oracle.py, pinned to the LDM encoder / decoder implementations inside the installed transformers by
+tests/test_vae_oracle_pin.py).
 
 STATUS: validated on a B200 in round 2 (profiles/r02_first_call.log); collected by the default -m gpu run.  The host orchestration is covered on CPU by tests/test_vae_oracle.py."""
 import os

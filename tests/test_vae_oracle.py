@@ -1,5 +1,6 @@
-"""CPU: the VAE restatement (oracle/vae_oracle.py, SURVEY.md §8f row 2 — diffusers is absent: PARITY UNPINNED, the
-only external anchor is the SD-1.x VAE's parameter count), the native container's state-dict contract, and the
+"""CPU: the VAE restatement (oracle/vae_oracle.py, SURVEY.md §8f row 2 — pinned to transformers' LDM encoder /
+decoder implementations by tests/test_vae_oracle_pin.py, and to the SD-1.x VAE's parameter count here), the native
+container's state-dict contract, and the
 VaeEngine host orchestration against the restatement through the CPU statement of the kernel contracts."""
 import pytest
 import torch
