@@ -486,14 +486,15 @@ template <int NCH, int BKV, int KST, int ONES, bool SPLIT = false, bool TRACE = 
 static int launch_attn(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a,
                        cudaStream_t stream) {
   using Cfg = AttnCfg<NCH, BKV, KST>;
-  static bool attr_set = false;
+  static unsigned long long attr_set_mask = 0;   // bit d: attribute set on device d (it is a per-device property)
+  const bool attr_set = ((attr_set_mask >> (ctx->device & 63)) & 1ull) != 0;
   p.trace = TRACE ? g_attn_trace : nullptr;
   p.trace_cap = TRACE ? g_attn_trace_cap : 0;
   if (!attr_set) {
     MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<NCH, BKV, KST, ONES, SPLIT, TRACE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set_mask |= 1ull << (ctx->device & 63);
   }
   if (encode_attn_maps(p, a, BKV)) return -1;
   p.n_kv_tiles = (a->lkv + BKV - 1) / BKV;
@@ -857,12 +858,13 @@ template <int NCH, int BKV, int KST, bool ONES>
 static int launch_attn_pp(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a,
                           cudaStream_t stream) {
   using Cfg = AttnPPCfg<NCH, BKV, KST>;
-  static bool attr_set = false;
+  static unsigned long long attr_set_mask = 0;   // bit d: attribute set on device d (it is a per-device property)
+  const bool attr_set = ((attr_set_mask >> (ctx->device & 63)) & 1ull) != 0;
   if (!attr_set) {
     MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_pp_kernel<NCH, BKV, KST, ONES>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set_mask |= 1ull << (ctx->device & 63);
   }
   if (encode_attn_maps(p, a, BKV)) return -1;
   p.n_kv_tiles = (a->lkv + BKV - 1) / BKV;
@@ -1207,12 +1209,13 @@ template <int KST, bool ONES>
 static int launch_attn_sk(const mdk_ctx* ctx, AttnParams& p, const mdk_attn_args* a,
                           cudaStream_t stream) {
   using Cfg = AttnCfg<1, SK_BKV, KST>;
-  static bool attr_set = false;
+  static unsigned long long attr_set_mask = 0;   // bit d: attribute set on device d (it is a per-device property)
+  const bool attr_set = ((attr_set_mask >> (ctx->device & 63)) & 1ull) != 0;
   if (!attr_set) {
     MDK_CHECK_CUDA(cudaFuncSetAttribute(attn_sk_kernel<KST, ONES>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set_mask |= 1ull << (ctx->device & 63);
   }
   if (encode_attn_maps(p, a, SK_BKV)) return -1;
   p.n_kv_tiles = (a->lkv + SK_BKV - 1) / SK_BKV;

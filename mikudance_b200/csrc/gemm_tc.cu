@@ -682,7 +682,8 @@ static int pow2_div(int x, int cap) {
 template <int BN, int CG>
 static int launch_gemm(const mdk_ctx* ctx, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
-  static bool attr_set = false;  // per kernel instantiation; benign race (idempotent)
+  static unsigned long long attr_set_mask = 0;   // bit d: attribute set on device d (it is a per-device property)
+  const bool attr_set = ((attr_set_mask >> (ctx->device & 63)) & 1ull) != 0;
   static int max_clusters = 0;
   if (!attr_set) {
     MDK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>,
@@ -706,7 +707,7 @@ static int launch_gemm(const mdk_ctx* ctx, const GemmParams& p, cudaStream_t str
       MDK_REQUIRE(n > 0, "mdk_gemm_f16: no CTA pair of the 2-CTA GEMM fits on this device");
       max_clusters = n < ctx->num_sms / 2 ? n : ctx->num_sms / 2;
     }
-    attr_set = true;
+    attr_set_mask |= 1ull << (ctx->device & 63);
   }
   const int total = p.mp_tiles * p.n_tiles;
   if (CG == 2) {

@@ -476,13 +476,14 @@ extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void
       t.seg = seg;
       t.rs = rs;
       t.scale_log2 = a->scale * 1.4426950408889634f;
-      static bool tile_attr = false;
+      static unsigned long long tile_attr_mask = 0;
+      const bool tile_attr = ((tile_attr_mask >> (ctx->device & 63)) & 1ull) != 0;
       if (!tile_attr) {
         MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_tile_kernel<1>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_tile_kernel<2>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        tile_attr = true;
+        tile_attr_mask |= 1ull << (ctx->device & 63);
       }
       const long long grid = static_cast<long long>(a->nb) * a->npix * (a->heads / hg);
       MDK_REQUIRE(grid < (1ll << 31), "mdk_temporal_attn_f16: grid too large");
@@ -553,13 +554,14 @@ extern "C" int mdk_temporal_attn_f16(mdk_ctx* ctx, const mdk_tattn_args* a, void
   long long ctas = (groups + warps - 1) / warps;
   const long long cap = static_cast<long long>(ctx->num_sms) * 8;
   if (ctas > cap) ctas = cap;
-  static bool attr_set = false;
+  static unsigned long long attr_set_mask = 0;   // bit d: attribute set on device d (it is a per-device property)
+  const bool attr_set = ((attr_set_mask >> (ctx->device & 63)) & 1ull) != 0;
   if (!attr_set) {
     MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_kernel<16>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MDK_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_kernel<32>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_set_mask |= 1ull << (ctx->device & 63);
   }
   if (a->f_kv <= 16)
     temporal_attn_kernel<16><<<static_cast<unsigned>(ctas), warps * 32, smem, stream>>>(p);
