@@ -170,6 +170,13 @@ __global__ void __launch_bounds__(A2S_THREADS, 2) attn_2s_kernel(const __grid_co
         // unit 0: K_0
         mbar_wait(q_bar, 0);
         mbar_wait(&u_full[0], 0);
+        if (p.stagger > 0) {
+          // de-phase the streams: identical work per tile keeps streams that start together in lock-step (all in
+          // their exp2 loops at once, then all waiting for the tensor core at once)
+          const long long t_end = clock64() + static_cast<long long>(p.stagger) * (g + 2 * (blockIdx.x & 1));
+          while (clock64() < t_end) {
+          }
+        }
         tc_fence_after();
         for (int ks = 0; ks < dk16; ++ks)
           tc_mma_f16_ss(tS, qdesc + 2u * ks, kdesc0 + 2u * ks, idesc_s, ks > 0 ? 1u : 0u);

@@ -158,6 +158,11 @@ __global__ void __launch_bounds__(A32_THREADS, 2) attn_2s32_kernel(const __grid_
         };
         mbar_wait(q_bar, 0);
         mbar_wait(&u_full[0], 0);
+        if (p.stagger > 0) {   // de-phase the streams (see attn_2s.cu)
+          const long long t_end = clock64() + static_cast<long long>(p.stagger) * (g + 2 * (blockIdx.x & 1));
+          while (clock64() < t_end) {
+          }
+        }
         tc_fence_after();
         issue_s(0, kdesc0);
         if (nh > 1) issue_s(1, kdesc0);

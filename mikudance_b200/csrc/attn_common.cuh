@@ -44,6 +44,7 @@ struct AttnParams {
   int poly;          // 1: every second pair of exponentials on the FMA pipe (ex2_poly_h2)
   long long* trace;  // TRACE instantiation only: clock64 timeline of one CTA, [tile][16 slots]
   int trace_cap;     // tiles the trace buffer holds
+  int stagger;       // two-stream kernels: cycles by which stream 1 (and odd CTAs, x2) start late (MDK_ATTN_STAGGER)
 };
 
 

@@ -1283,15 +1283,21 @@ extern "C" int mdk_attn_fwd_f16(mdk_ctx* ctx, const mdk_attn_args* a, void* stre
     if (a->d > 64 && a->d <= 128 && (pp & 2)) return launch_attn_pp<2, 64, 3, false>(ctx, p, a, stream);
   }
   if (a->d <= 64) {
-    // Two softmax streams per CTA, P in tensor memory (attn_2s.cu): the default for long key sequences with the
-    // ones-row V^T (the L0 spatial self-attention: 1.74-1.78 ms vs 1.92 ms for 8 images of 9216 tokens, d = 40),
-    // with every fourth pair of exponentials on the FMA pipe.  The 257-token cross-attention stays on the
-    // one-stream kernels (2.73 vs 2.93 ms per step).  MDK_ATTN_2S=0 switches it off, =1 forces it for every
-    // head_dim <= 64 problem, =2 the self-issuing variant; MDK_ATTN_POLY overrides the polynomial share.
+    // Two softmax streams per CTA, P in tensor memory, 32-key sub-tiles (attn_2s32.cu): the default for long key
+    // sequences with the ones-row V^T (the L0 spatial self-attention: 1.81 ms vs 1.87 ms for attn_2s.cu and 1.94 ms
+    // for the one-stream kernel, 8 images of 9216 tokens, d = 40, medians of alternating runs under the power
+    // cap), with every fourth pair of exponentials on the FMA pipe.  The 257-token cross-attention stays on the
+    // one-stream kernels (2.73 vs 2.93 ms per step).  MDK_ATTN_2S=0 switches it off; =1 attn_2s.cu (64-key
+    // chunks), =2 its self-issuing variant, =3 attn_2s32.cu, each for every head_dim <= 64 problem;
+    // MDK_ATTN_POLY overrides the polynomial share, MDK_ATTN_STAGGER de-phases the streams (no gain measured).
     const char* e = getenv("MDK_ATTN_2S");
-    const int two = e ? atoi(e) : ((a->vt_ones && a->lkv >= 1024 && a->lq >= 256) ? 1 : 0);
+    const int two = e ? atoi(e) : ((a->vt_ones && a->lkv >= 1024 && a->lq >= 256) ? 3 : 0);
     if (two) {
       if (!getenv("MDK_ATTN_POLY") && a->vt_ones) p.poly = 1;
+      {
+        const char* es = getenv("MDK_ATTN_STAGGER");
+        p.stagger = es ? atoi(es) : 0;
+      }
       if (two == 3) return launch_attn_2s32(ctx, p, a, stream);   // 32-key sub-tiles (attn_2s32.cu)
       const char* etr = getenv("MDK_ATTN_TRACE");
       const bool trace = etr && atoi(etr) && g_attn_trace != nullptr;

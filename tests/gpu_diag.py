@@ -885,7 +885,26 @@ def ab_attn_switches():
     vt2 = vt2.reshape(nimg, heads * dp, l)
     out = torch.empty_like(q)
     names = ("MDK_ATTN_POLY", "MDK_ATTN_SK", "MDK_ATTN_PP", "MDK_ATTN_BKV", "MDK_ATTN_STALE", "MDK_ATTN_SPLITKV",
-             "MDK_ATTN_2S")
+             "MDK_ATTN_2S", "MDK_ATTN_STAGGER")
+    if os.environ.get("MDK_AB_STAGGER", "0") == "1":
+        # stream de-phasing experiment: alternate the candidates several times (clock / power noise is +-3 %)
+        res = {}
+        cands = [{}, {"MDK_ATTN_STAGGER": "300"}, {"MDK_ATTN_STAGGER": "600"}, {"MDK_ATTN_STAGGER": "1200"},
+                 {"MDK_ATTN_2S": "3"}, {"MDK_ATTN_2S": "3", "MDK_ATTN_STAGGER": "300"},
+                 {"MDK_ATTN_2S": "3", "MDK_ATTN_STAGGER": "600"}]
+        for rep in range(4):
+            for env in cands:
+                for n in names:
+                    os.environ.pop(n, None)
+                os.environ.update(env)
+                ms = timeit_ms(lambda: ops.attention(q, k, vt2, nimg=nimg, lq=l, lkv=l, heads=heads, d=d, out=out,
+                                                     vt_head_rows=dp, vt_ones=True))
+                res.setdefault(str(env), []).append(ms)
+        for kk, v in res.items():
+            print(f"perf attn(ones) {kk}: " + " ".join(f"{x:.3f}" for x in v) + f"  median {sorted(v)[len(v) // 2]:.3f} ms", flush=True)
+        for n in names:
+            os.environ.pop(n, None)
+        return True
     extra = ({"MDK_ATTN_SPLITKV": "1"}, {"MDK_ATTN_SPLITKV": "1", "MDK_ATTN_POLY": "1"},
              {"MDK_ATTN_2S": "1"}, {"MDK_ATTN_2S": "1", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_2S": "1", "MDK_ATTN_POLY": "2"},
              {"MDK_ATTN_2S": "2"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "1"}, {"MDK_ATTN_2S": "2", "MDK_ATTN_POLY": "2"},
