@@ -65,27 +65,37 @@ struct GemmParams {
   int dbg;  // MDK_GEMM_DEBUG bit 1 (perf triage only): skip the global stores of the epilogue
 };
 
-template <int BN, int CG>
+// BS ("B stationary", CG == 1, plain GEMM with K <= 320): the BN x K weight panel stays resident in shared memory and
+// only the A tiles stream through the ring.  Tiles are walked n-major (all M tiles of one N tile before the next), so a
+// persistent CTA reloads the panel once or twice per launch.  Why: the K = 320 linears of level 0 (M = 294 912) are
+// bound by the L2 -> SM fill rate, not by HBM or the tensor pipe — ncu: 8.9 TB/s of L2 -> SM traffic, 28 % tensor,
+// 2.7 TB/s DRAM — because every 128 x 160 tile re-stages its 100 KB weight panel next to 80 KB of A.
+constexpr int BS_KB = 5;   // k-blocks of a resident panel (K <= 320)
+
+template <int BN, int CG, bool BS = false>
 struct GemmCfg {
   static constexpr int B_ROWS = BN / CG;                  // B rows this CTA stages
   static constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGE_BYTES = BS ? A_TILE_BYTES : A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int EPI_STAGING = EPI_WARPS * 2 * 32 * 64;  // per epilogue warp: output + residual sub-tile
   static constexpr int EPI_BIAS = EPI_WARPS * 256;  // per epilogue warp: bias of the current chunk(s)
-  static constexpr int RING_BUDGET = 232448 - EPI_STAGING - EPI_BIAS - 256;
+  static constexpr int PANEL_BYTES = BS ? BS_KB * B_TILE_BYTES : 0;
+  static constexpr int RING_BUDGET = 232448 - EPI_STAGING - EPI_BIAS - 256 - PANEL_BYTES;
   static constexpr int STAGES_CG1 = (BN >= 192) ? 4 : (BN >= 160 ? 5 : 6);
   static constexpr int STAGES_FIT = RING_BUDGET / STAGE_BYTES;
-  static constexpr int STAGES = (CG == 1) ? STAGES_CG1 : (STAGES_FIT > 8 ? 8 : STAGES_FIT);
+  static constexpr int STAGES = BS ? (STAGES_FIT > 8 ? 8 : STAGES_FIT)
+                                   : ((CG == 1) ? STAGES_CG1 : (STAGES_FIT > 8 ? 8 : STAGES_FIT));
+  static_assert(!BS || (CG == 1 && STAGES >= 3), "B-stationary: single CTA, at least 3 A stages");
   static constexpr int TMEM_COLS = (2 * BN <= 32)    ? 32
                                    : (2 * BN <= 64)  ? 64
                                    : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256
                                                      : 512;
   // dynamic shared memory is declared __align__(1024) (checked at run time): no alignment slack
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING + EPI_BIAS + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PANEL_BYTES + EPI_STAGING + EPI_BIAS + 256 /*barriers*/;
   static_assert(B_TILE_BYTES % 1024 == 0, "B stage tiles must keep the 1024-byte swizzle alignment");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  static_assert(2 * STAGES + 4 <= 30, "barrier block");
+  static_assert(2 * STAGES + 5 <= 30, "barrier block");
 };
 
 // GELU with the exact (erf) formulation of diffusers' GEGLU, x * Phi(x), evaluated as
@@ -167,10 +177,10 @@ __device__ __forceinline__ void store_chunk_tma(const float (&o)[32], uint32_t b
   }
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool BS = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, BS>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;  // 1024-byte alignment required by the 128B swizzle atoms
@@ -179,15 +189,16 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     __trap();
   }
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
-  uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;     // BS: the resident panel (BS_KB k-block slices)
+  uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES + Cfg::PANEL_BYTES;
   uint8_t* smem_bias = smem_epi + Cfg::EPI_STAGING;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + Cfg::EPI_BIAS);
   uint64_t* full_bar = bars;                     // [STAGES]
   uint64_t* empty_bar = bars + STAGES;           // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* bfull_bar = bars + 2 * STAGES + 4;   // [1] BS: the weight panel has landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -210,6 +221,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], EPI_WARPS * CG);  // one arrive per epilogue warp (of both CTAs)
     }
+    mbar_init(bfull_bar, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -242,10 +254,22 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       uint32_t phase = 0;
       // pair mode: transaction bytes of both CTAs are counted on the leader's full barrier
       const uint32_t full0_cluster = (CG == 2) ? mapa_shared(smem_u32(&full_bar[0]), 0) : 0u;
+      int cur_n = -1, last_stage = -1;   // BS: N tile of the resident panel; stage / phase of the last A load
+      uint32_t last_phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = (tile / p.n_tiles) * CG + cta_rank;   // may be a phantom tile past M (zero-filled)
+        const int n_tile = BS ? tile / p.mp_tiles : tile % p.n_tiles;
+        const int m_tile = BS ? tile % p.mp_tiles : (tile / p.n_tiles) * CG + cta_rank;   // may be a phantom tile past M
         const int n0 = n_tile * BN + cta_rank * Cfg::B_ROWS;      // pair mode: this CTA's half of the B tile
+        if constexpr (BS) {
+          if (n_tile != cur_n) {
+            // every MMA that reads the old panel has retired once the last A stage handed out is free again
+            if (last_stage >= 0) mbar_wait(&empty_bar[last_stage], last_phase);
+            mbar_expect_tx(bfull_bar, static_cast<uint32_t>(num_kb) * Cfg::B_TILE_BYTES);
+            for (int kb = 0; kb < num_kb; ++kb)
+              tma_load_2d(smem_b + kb * Cfg::B_TILE_BYTES, &p.tmB, bfull_bar, kb * BK, n0);
+            cur_n = n_tile;
+          }
+        }
         int m0 = m_tile * BM;
         int img0 = 0, h0 = 0, w0 = 0;
         if (p.taps > 1) {
@@ -282,7 +306,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
               } else {
                 tma_load_2d(smem_a + stage * A_TILE_BYTES, ta, &full_bar[stage], kk, m0);
               }
-              tma_load_2d(smem_b + stage * Cfg::B_TILE_BYTES, &p.tmB, &full_bar[stage], bcol, n0);
+              if constexpr (!BS) tma_load_2d(smem_b + stage * Cfg::B_TILE_BYTES, &p.tmB, &full_bar[stage], bcol, n0);
+              last_stage = stage;
+              last_phase = phase;
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -299,8 +325,17 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     uint32_t phase = 0;
     uint32_t acc_phase[2] = {0, 0};
     int it = 0;
+    int cur_n = -1;          // BS: N tile of the resident panel
+    uint32_t bphase = 0;
     for (int tile = (cta_rank == 0) ? first_tile : total_tiles; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
+      if constexpr (BS) {
+        if (tile / p.mp_tiles != cur_n) {
+          mbar_wait(bfull_bar, bphase);
+          bphase ^= 1u;
+          cur_n = tile / p.mp_tiles;
+        }
+      }
       mbar_wait(&tempty_bar[acc], acc_phase[acc] ^ 1u);
       acc_phase[acc] ^= 1u;
       tc_fence_after();
@@ -310,7 +345,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         tc_fence_after();
         if (elect_one()) {
           const uint64_t adesc = make_sdesc_sw128(smem_u32(smem_a + stage * A_TILE_BYTES));
-          const uint64_t bdesc = make_sdesc_sw128(smem_u32(smem_b + stage * Cfg::B_TILE_BYTES));
+          const uint64_t bdesc = make_sdesc_sw128(smem_u32(smem_b + (BS ? kb : stage) * Cfg::B_TILE_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
@@ -350,8 +385,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     const uint32_t tempty0_cluster = (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = (tile / p.n_tiles) * CG + cta_rank;
+      const int n_tile = BS ? tile / p.mp_tiles : tile % p.n_tiles;
+      const int m_tile = BS ? tile % p.mp_tiles : (tile / p.n_tiles) * CG + cta_rank;
       const int n0 = n_tile * BN;
       long long m;  // global output row of this thread, -1 if out of range
       if (p.taps > 1) {
@@ -594,29 +629,69 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             } else {
               store_chunk_coalesced(o, stage_addr, lane, m32, obase, ldo, seg_col0 + c, nvalid);
             }
-          } else if (m >= 0) {
-            // per-image transposed store: lanes hold consecutive rows -> 64-byte runs per column
-            const long long img = m / p.trans_rows;
-            const long long l = m % p.trans_rows;
-            if (p.trans_head_dp > 0) {
-              // channel (seg_col0 + c + j) = head * d + w  ->  row head * dp + w of this image
-              const int hd = p.trans_head_d, hdp = p.trans_head_dp;
-              int head = (seg_col0 + c) / hd, wch = (seg_col0 + c) % hd;
-              __half* ibase = obase + img * (p.seg_cols / hd) * hdp * p.trans_ld + l;
+          } else {
+            // per-image transposed store (V^T for the attention kernels).  Fast path — the warp's 32 rows are 32
+            // consecutive, 8-aligned positions of ONE image: the 32 x 32 sub-tile is transposed through the warp's
+            // staging buffer ([column][row], 64 B per column) and written as 16-byte pieces, 8 columns x 64 B per
+            // store instruction (the direct path below issues 32 two-byte stores per lane: 207 TFLOP/s on the
+            // level-0 k|v^T projection where the plain GEMM reaches 620).
+            const int m_first = __shfl_sync(0xffffffffu, m32, 0);
+            const int m_last = __shfl_sync(0xffffffffu, m32, 31);
+            const int l_first = (m_first >= 0) ? m_first % p.trans_rows : -1;
+            const bool fast = m_first >= 0 && m_last == m_first + 31 && (l_first & 7) == 0 &&
+                              l_first + 32 <= p.trans_rows && (p.trans_ld & 7) == 0 && nvalid == 32 &&
+                              (reinterpret_cast<uintptr_t>(obase) & 15) == 0;
+            if (fast) {
+              if (p.tma_store && leader) bulk_wait_read<0>();   // an earlier TMA store may still read the buffer
+              __syncwarp();
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                if (j < nvalid)
-                  ibase[static_cast<long long>(head * hdp + wch) * p.trans_ld] = __float2half_rn(o[j]);
-                if (++wch == hd) {
-                  wch = 0;
-                  ++head;
-                }
+                const __half hv = __float2half_rn(o[j]);
+                asm volatile("st.shared.u16 [%0], %1;\n" ::"r"(stage_addr + static_cast<uint32_t>(j) * 64u +
+                                                               static_cast<uint32_t>(lane) * 2u),
+                             "h"(*reinterpret_cast<const unsigned short*>(&hv))
+                             : "memory");
               }
-            } else {
-              __half* dst = obase + (img * p.seg_cols + seg_col0 + c) * p.trans_ld + l;
+              __syncwarp();
+              const long long img = m_first / p.trans_rows;
+              const int hd = p.trans_head_d, hdp = p.trans_head_dp;
+              const long long rows_per_img = (hdp > 0) ? static_cast<long long>(p.seg_cols / hd) * hdp : p.seg_cols;
+              __half* ibase = obase + img * rows_per_img * p.trans_ld + l_first;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j < nvalid) dst[static_cast<long long>(j) * p.trans_ld] = __float2half_rn(o[j]);
+              for (int i = 0; i < 4; ++i) {
+                const int col = i * 8 + (lane >> 2);      // column of the sub-tile
+                const int piece = lane & 3;               // 8 rows = 16 bytes
+                const int ch = seg_col0 + c + col;        // channel inside the segment
+                const long long vrow = (hdp > 0) ? static_cast<long long>(ch / hd) * hdp + (ch % hd) : ch;
+                uint4 val;
+                ld_shared_v4(stage_addr + static_cast<uint32_t>(col) * 64u + static_cast<uint32_t>(piece) * 16u, val);
+                *reinterpret_cast<uint4*>(ibase + vrow * p.trans_ld + piece * 8) = val;
+              }
+              __syncwarp();
+            } else if (m >= 0) {
+              // direct path: lanes hold consecutive rows -> 64-byte runs per column
+              const long long img = m / p.trans_rows;
+              const long long l = m % p.trans_rows;
+              if (p.trans_head_dp > 0) {
+                // channel (seg_col0 + c + j) = head * d + w  ->  row head * dp + w of this image
+                const int hd = p.trans_head_d, hdp = p.trans_head_dp;
+                int head = (seg_col0 + c) / hd, wch = (seg_col0 + c) % hd;
+                __half* ibase = obase + img * (p.seg_cols / hd) * hdp * p.trans_ld + l;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (j < nvalid)
+                    ibase[static_cast<long long>(head * hdp + wch) * p.trans_ld] = __float2half_rn(o[j]);
+                  if (++wch == hd) {
+                    wch = 0;
+                    ++head;
+                  }
+                }
+              } else {
+                __half* dst = obase + (img * p.seg_cols + seg_col0 + c) * p.trans_ld + l;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (j < nvalid) dst[static_cast<long long>(j) * p.trans_ld] = __float2half_rn(o[j]);
+                }
               }
             }
           }
@@ -679,14 +754,14 @@ static int pow2_div(int x, int cap) {
   return r;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool BS = false>
 static int launch_gemm(const mdk_ctx* ctx, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, BS>;
   static unsigned long long attr_set_mask = 0;   // bit d: attribute set on device d (it is a per-device property)
   const bool attr_set = ((attr_set_mask >> (ctx->device & 63)) & 1ull) != 0;
   static int max_clusters = 0;
   if (!attr_set) {
-    MDK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>,
+    MDK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, BS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     if (CG == 2) {
@@ -703,7 +778,7 @@ static int launch_gemm(const mdk_ctx* ctx, const GemmParams& p, cudaStream_t str
       qc.attrs = qa;
       qc.numAttrs = 1;
       int n = 0;
-      MDK_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, CG>, &qc));
+      MDK_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, CG, BS>, &qc));
       MDK_REQUIRE(n > 0, "mdk_gemm_f16: no CTA pair of the 2-CTA GEMM fits on this device");
       max_clusters = n < ctx->num_sms / 2 ? n : ctx->num_sms / 2;
     }
@@ -726,12 +801,12 @@ static int launch_gemm(const mdk_ctx* ctx, const GemmParams& p, cudaStream_t str
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    MDK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, p));
+    MDK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, BS>, p));
     count_launch();
     return 0;
   }
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  MDK_CHECK_CUDA(launch_pdl(gemm_tc_kernel<BN, CG>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p));
+  MDK_CHECK_CUDA(launch_pdl(gemm_tc_kernel<BN, CG, BS>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p));
   count_launch();
   return 0;
 }
@@ -938,6 +1013,22 @@ extern "C" int mdk_gemm_f16(mdk_ctx* ctx, const mdk_gemm_args* a, void* stream_)
   }
 
   p.mp_tiles = (p.m_tiles + cg - 1) / cg;
+  {
+    // B-stationary kernel: plain single-source GEMM, K <= 320, single CTA, and enough M tiles per SM that the panel
+    // (re)load amortises (level 0: 2 304 M tiles).  MDK_GEMM_BS=1 switches it on (2: for every eligible M).
+    const char* e = getenv("MDK_GEMM_BS");   // read per call: tests switch kernels in-process
+    const int bs = e ? atoi(e) : 0;   // measured (profiles/r02_gemm_bstationary.log): no gain — 0.098 vs 0.090 ms for
+                                      // M = 294 912, N = K = 320; the step is unchanged — so it is off by default
+    if (bs && cg == 1 && a->conv_taps == 1 && a->k1 == 0 && !a->geglu && K <= BS_KB * BK &&
+        (bs == 2 || p.mp_tiles >= 4 * ctx->num_sms)) {   // (= 2: regardless of M, for the parity tests)
+      switch (bn) {
+        case 192: return launch_gemm<192, 1, true>(ctx, p, stream);
+        case 160: return launch_gemm<160, 1, true>(ctx, p, stream);
+        case 128: return launch_gemm<128, 1, true>(ctx, p, stream);
+        default: break;
+      }
+    }
+  }
   if (cg == 2) {
     switch (bn) {
       case 256: return launch_gemm<256, 2>(ctx, p, stream);

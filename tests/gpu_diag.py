@@ -130,6 +130,22 @@ def check_gemm_epilogue():
     got = vtp.reshape(nimg, 8, 48, Lp)[:, :, :40, :L].reshape(nimg, 320, L).permute(0, 2, 1).reshape(M2, 320)
     ok &= report("seg vT padded heads", got, ref3[:, 640:])
     pad_ok = bool((vtp.reshape(nimg, 8, 48, Lp)[:, :, 40:, :] == 7.0).all())
+    # 32-row-aligned images: the smem-transposed 16-byte store path of the V^T epilogue (dense and padded heads)
+    for La in (256, 1152):
+        Ma = 2 * La
+        a3 = rnd(Ma, K, seed=31).to(F16)
+        qa = torch.empty(Ma, 320, dtype=F16, device=DEV)
+        ka = torch.empty(Ma, 320, dtype=F16, device=DEV)
+        vta = torch.zeros(2, 320, La, dtype=F16, device=DEV)
+        ops.gemm(a3, w3, outs=[qa, ka, vta], trans=[False, False, True], trans_rows=La)
+        refa = a3.float() @ w3.float().t()
+        ok &= report(f"seg vT aligned L={La}", vta.permute(0, 2, 1).reshape(Ma, 320), refa[:, 640:])
+        ok &= report(f"seg k aligned L={La}", ka, refa[:, 320:640])
+        vtpa = torch.full((2, 8 * 48, La), 7.0, dtype=F16, device=DEV)
+        ops.gemm(a3, w3, outs=[qa, ka, vtpa], trans=[False, False, True], trans_rows=La, trans_head=(40, 48))
+        gota = vtpa.reshape(2, 8, 48, La)[:, :, :40].reshape(2, 320, La).permute(0, 2, 1).reshape(Ma, 320)
+        ok &= report(f"seg vT aligned padded heads L={La}", gota, refa[:, 640:])
+        ok &= bool((vtpa.reshape(2, 8, 48, La)[:, :, 40:] == 7.0).all())
     print(f"[{'OK ' if pad_ok else 'BAD'}] seg vT pad rows untouched", flush=True)
     return ok and pad_ok
 
@@ -166,6 +182,25 @@ def check_conv():
     out = ops.gemm(col, wp)
     ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).float(), wt.float(), stride=2, padding=1)
     ok &= report("conv stride2 (im2col)", out, ref.permute(0, 2, 3, 1).reshape(-1, cout))
+    return ok
+
+
+def check_gemm_bs_l0():
+    """Level-0 linear shapes (many M tiles per SM, 2 / 5 / 6 N tiles: the resident weight panel is reloaded) on the
+    B-stationary kernel: bias + residual, row bias, q|k|v^T segments."""
+    ok = True
+    M, K = 128 * 148 * 5 + 77, 320
+    a = rnd(M, K).to(F16)
+    for N in (320, 960):
+        w = rnd(N, K, scale=K ** -0.5).to(F16)
+        bias = rnd(N)
+        res = rnd(M, N, seed=3).to(F16)
+        ref = a.float() @ w.float().t() + bias
+        ok &= report(f"bs gemm M={M} N={N} K={K} bias+res", ops.gemm(a, w, bias=bias, residual=res), ref + res.float())
+    rb = rnd(7, 960)
+    w = rnd(960, K, scale=K ** -0.5).to(F16)
+    rows = torch.arange(M, device=DEV)
+    ok &= report("bs gemm row_bias", ops.gemm(a, w, row_bias=rb, row_div=4096), a.float() @ w.float().t() + rb[(rows // 4096) % 7])
     return ok
 
 
@@ -1022,7 +1057,7 @@ CHECKS = {
     "perf_vae_clip": perf_vae_clip, "vae": check_vae, "vae_sd": check_vae_sd, "clip": check_clip, "clip_vitl14": check_clip_vitl14, "trace_attn": trace_attn, "trace_attn_2s": trace_attn_2s, "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
     "refunet_ops": check_refunet_ops, "refunet_tiny": check_refunet_tiny, "refunet_a": check_refunet_a,
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,
-    "gemm_basic": check_gemm_basic, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
+    "gemm_basic": check_gemm_basic, "gemm_bs_l0": check_gemm_bs_l0, "gemm_epilogue": check_gemm_epilogue, "conv": check_conv,
     "norms": check_norms, "temporal": check_temporal, "misc": check_misc, "attn": check_attn,
     "perf_gemm": perf_gemm, "perf_attn": perf_attn, "ncu_gemm": ncu_gemm, "ncu_gemm2": ncu_gemm2, "perf_gemm_small": perf_gemm_small, "perf_misc": perf_misc, "ncu_attn": ncu_attn,
 }

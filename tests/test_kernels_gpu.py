@@ -81,6 +81,16 @@ def test_gemm_single_cta_and_cta_pair_kernels(monkeypatch, cg):
     assert D.check_conv()
 
 
+def test_gemm_b_stationary_kernel(monkeypatch):
+    """The weight-stationary GEMM kernel (K <= 320, single CTA; picked by itself only for M >= 75 776) forced on every
+    eligible shape / epilogue of the GEMM checks, plus the level-0 shape it is meant for."""
+    monkeypatch.setenv("MDK_GEMM_BS", "2")
+    monkeypatch.setenv("MDK_GEMM_CG", "1")
+    assert D.check_gemm_basic()
+    assert D.check_gemm_epilogue()
+    assert D.check_gemm_bs_l0()
+
+
 def test_argument_errors_are_reported():
     from mikudance_b200 import _lib
     a = torch.randn(64, 36, device="cuda").half()          # K = 36 is not a multiple of 8
