@@ -26,6 +26,7 @@ struct GnParams {
   float* ws;  // [nimg, GN_MAX_CHUNKS, groups, 2] per-CTA partial (sum, sumsq)
   int pix_per_cta;
   int nchunks;
+  int stage_pix;       // bulk kernels: pixels per shared-memory stage
   int out_chunk_pix;   // > 0: exchange layout [chunk, nimg_total, out_chunk_pix, C] (see mdk.h)
   int nimg_total;      // images of the whole call (the launch may cover a sub-range starting at img0)
   int img0;
@@ -220,6 +221,232 @@ __global__ void gn_apply_kernel(const GnParams p) {
         store8(p.out + orow * p.C + ch, v);
       }
     }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Bulk-copy variants (MDK_GN_BULK=1; measured time-neutral, so off by default): the CTA's pixel slab is contiguous in memory per source, so one elected thread
+// streams it through a GN_STAGES-deep shared-memory ring with cp.async.bulk (1-D bulk copies signalled on
+// mbarriers) and the threads read their channel vectors from shared memory.  Why: ncu on the register-staged
+// kernels above (profiles/r02_ncu_norms_metrics.txt) — 54-56 registers x 480 threads = 2 CTAs per SM, 4 loads of
+// 16 bytes in flight per thread = 61 KB per SM: 3.3 TB/s (stats) and 4.0 TB/s (apply) of the 6.5 TB/s copy
+// bandwidth; 8 loads per thread need 88 registers and halve the occupancy (measured: slower).  With the ring the
+// bytes in flight (GN_STAGES x ~16 KB per CTA) do not live in registers.  Result: parity-green, same time — bytes
+// in flight were not the limit either; what helps the small levels is fewer, longer CTAs (MDK_GN_OVERSUB).
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_STAGES = 4;
+constexpr int GN_STAGE_BYTES = 16384;
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_smem),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// stage layout: [stage_pix x c0 halves | stage_pix x c1 halves]
+struct GnRing {
+  uint8_t* base;
+  uint64_t* full;
+  int pbeg, pend, nst;   // slab [pbeg, pend), number of stages of stage_pix pixels
+};
+
+__device__ __forceinline__ void gn_issue_stage(const GnParams& p, const GnRing& r, int img, int it) {
+  const int px0 = r.pbeg + it * p.stage_pix;
+  const int npx = min(p.stage_pix, r.pend - px0);
+  const int slot = it % GN_STAGES;
+  uint8_t* dst = r.base + slot * GN_STAGE_BYTES;
+  const uint32_t b0 = static_cast<uint32_t>(npx) * p.c0 * 2u;
+  const uint32_t b1 = static_cast<uint32_t>(npx) * p.c1 * 2u;
+  mbar_expect_tx(&r.full[slot], b0 + b1);
+  bulk_load_1d(smem_u32(dst), p.x0 + (static_cast<long long>(img) * p.hw + px0) * p.c0, b0, &r.full[slot]);
+  if (p.c1 > 0)
+    bulk_load_1d(smem_u32(dst) + static_cast<uint32_t>(p.stage_pix) * p.c0 * 2u,
+                 p.x1 + (static_cast<long long>(img) * p.hw + px0) * p.c1, b1, &r.full[slot]);
+}
+
+__global__ void gn_stats_bulk_kernel(const GnParams p) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  float* s_red = reinterpret_cast<float*>(gsm + GN_STAGES * GN_STAGE_BYTES);   // [vy][vx][16] then col[2][C]
+  __shared__ uint64_t full[GN_STAGES];
+  const int img = blockIdx.y;
+  const int cv = threadIdx.x;
+  const int V = p.C >> 3;
+  const int vx = blockDim.x, vy = blockDim.y;
+  float* col = s_red + vy * vx * 16;
+  const int tid = threadIdx.y * vx + threadIdx.x;
+  GnRing r;
+  r.base = gsm;
+  r.full = full;
+  r.pbeg = blockIdx.x * p.pix_per_cta;
+  r.pend = min(p.hw, r.pbeg + p.pix_per_cta);
+  r.nst = (r.pend - r.pbeg + p.stage_pix - 1) / p.stage_pix;
+  if (tid == 0) {
+    for (int i = 0; i < GN_STAGES; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+  if (tid == 0)
+    for (int i = 0; i < GN_STAGES && i < r.nst; ++i) gn_issue_stage(p, r, img, i);
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  const int ch = cv * 8;
+  const bool from1 = ch >= p.c0;
+  const int cs = from1 ? p.c1 : p.c0;
+  const int soff = from1 ? p.stage_pix * p.c0 * 2 + (ch - p.c0) * 2 : ch * 2;
+  for (int it = 0; it < r.nst; ++it) {
+    const int slot = it % GN_STAGES;
+    mbar_wait(&full[slot], static_cast<uint32_t>((it / GN_STAGES) & 1));
+    const int npx = min(p.stage_pix, r.pend - (r.pbeg + it * p.stage_pix));
+    if (cv < V) {
+      const uint8_t* st = gsm + slot * GN_STAGE_BYTES + soff;
+      for (int px = threadIdx.y; px < npx; px += vy) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(st + static_cast<long long>(px) * cs * 2);
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          s[2 * e] += f.x;
+          q[2 * e] += f.x * f.x;
+          s[2 * e + 1] += f.y;
+          q[2 * e + 1] += f.y * f.y;
+        }
+      }
+    }
+    __syncthreads();   // every thread is done with the slot
+    if (tid == 0 && it + GN_STAGES < r.nst) gn_issue_stage(p, r, img, it + GN_STAGES);
+  }
+  float* mine = s_red + (threadIdx.y * vx + cv) * 16;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mine[e] = s[e];
+    mine[8 + e] = q[e];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && cv < V) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a = 0.f, b = 0.f;
+      for (int y = 0; y < vy; ++y) {
+        a += s_red[(y * vx + cv) * 16 + e];
+        b += s_red[(y * vx + cv) * 16 + 8 + e];
+      }
+      col[cv * 8 + e] = a;
+      col[p.C + cv * 8 + e] = b;
+    }
+  }
+  __syncthreads();
+  if (tid < p.groups) {
+    float a = 0.f, b = 0.f;
+    for (int c = tid * p.cpg; c < (tid + 1) * p.cpg; ++c) {
+      a += col[c];
+      b += col[p.C + c];
+    }
+    float* dst = p.ws + ((static_cast<long long>(img) * GN_MAX_CHUNKS + blockIdx.x) * p.groups + tid) * 2;
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+
+__global__ void gn_apply_bulk_kernel(const GnParams p) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  __shared__ uint64_t full[GN_STAGES];
+  __shared__ float s_mean[64], s_rstd[64];
+  float* s_part = reinterpret_cast<float*>(gsm + GN_STAGES * GN_STAGE_BYTES);   // [GN_MAX_CHUNKS * 64 * 2]
+  const int img = blockIdx.y;
+  const int cv = threadIdx.x;
+  const int V = p.C >> 3;
+  const int ch = cv * 8;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  GnRing r;
+  r.base = gsm;
+  r.full = full;
+  r.pbeg = blockIdx.x * p.pix_per_cta;
+  r.pend = min(p.hw, r.pbeg + p.pix_per_cta);
+  r.nst = (r.pend - r.pbeg + p.stage_pix - 1) / p.stage_pix;
+  if (tid == 0) {
+    for (int i = 0; i < GN_STAGES; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+  if (tid == 0)
+    for (int i = 0; i < GN_STAGES && i < r.nst; ++i) gn_issue_stage(p, r, img, i);
+  {
+    const float* part = p.ws + static_cast<long long>(img) * GN_MAX_CHUNKS * p.groups * 2;
+    const int n = p.nchunks * p.groups * 2;
+    for (int i = tid; i < n; i += nthr) s_part[i] = part[i];
+  }
+  __syncthreads();
+  if (tid < p.groups) {
+    double sum = 0.0, sq = 0.0;
+    for (int k = 0; k < p.nchunks; ++k) {
+      sum += static_cast<double>(s_part[(k * p.groups + tid) * 2]);
+      sq += static_cast<double>(s_part[(k * p.groups + tid) * 2 + 1]);
+    }
+    const double cnt = static_cast<double>(p.hw) * p.cpg;
+    const double mean = sum / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = static_cast<float>(mean);
+    s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+  }
+  __syncthreads();
+  float scale[8], shift[8];
+  if (cv < V) {
+    float gm[8], bt[8];
+    load8(p.gamma + ch, gm);
+    load8(p.beta + ch, bt);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int g = (ch + e) / p.cpg;
+      scale[e] = gm[e] * s_rstd[g];
+      shift[e] = bt[e] - s_mean[g] * scale[e];
+    }
+  }
+  const bool from1 = ch >= p.c0;
+  const int cs = from1 ? p.c1 : p.c0;
+  const int soff = from1 ? p.stage_pix * p.c0 * 2 + (ch - p.c0) * 2 : ch * 2;
+  const int vy = blockDim.y;
+  for (int it = 0; it < r.nst; ++it) {
+    const int slot = it % GN_STAGES;
+    mbar_wait(&full[slot], static_cast<uint32_t>((it / GN_STAGES) & 1));
+    const int px0 = r.pbeg + it * p.stage_pix;
+    const int npx = min(p.stage_pix, r.pend - px0);
+    if (cv < V) {
+      const uint8_t* st = gsm + slot * GN_STAGE_BYTES + soff;
+      for (int px = threadIdx.y; px < npx; px += vy) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(st + static_cast<long long>(px) * cs * 2);
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          v[2 * e] = f.x;
+          v[2 * e + 1] = f.y;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float y = v[e] * scale[e] + shift[e];
+          if (p.silu) y = __fdividef(y, 1.0f + __expf(-y));
+          v[e] = y;
+        }
+        const int pp = px0 + px;
+        long long orow = static_cast<long long>(img) * p.hw + pp;
+        if (p.out_chunk_pix > 0) {
+          const int d = pp / p.out_chunk_pix;
+          orow = (static_cast<long long>(d) * p.nimg_total + (p.img0 + img)) * p.out_chunk_pix + (pp - d * p.out_chunk_pix);
+        }
+        store8(p.out + orow * p.C + ch, v);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && it + GN_STAGES < r.nst) gn_issue_stage(p, r, img, it + GN_STAGES);
   }
 }
 
@@ -526,8 +753,16 @@ extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* strea
     q.out = (p.out_chunk_pix > 0) ? p.out : p.out + static_cast<long long>(i0) * a->hw * C;
     q.img0 = i0;
     q.ws = p.ws + static_cast<long long>(i0) * GN_MAX_CHUNKS * a->groups * 2;
-    // enough CTAs to fill the machine a few times over, at least one pixel row of work each
-    int chunks = (ctx->num_sms * 8 + ni - 1) / ni;
+    // CTAs per SM over the whole launch (MDK_GN_OVERSUB): both kernels fit 2 CTAs per SM; every CTA pays a fixed
+    // ~5 us (launch, partial-sum fetch / smem reduction tail) that is not overlapped by its only neighbour
+    static int oversub = -1;
+    if (oversub < 0) {
+      const char* e = getenv("MDK_GN_OVERSUB");
+      oversub = e ? atoi(e) : 3;   // measured (profiles/r02_gn_sweep.log): 3 -> 0.141 / 0.080 / 0.045 ms at L0 / L1 / L2,
+                                   // 8 (round 1) -> 0.140 / 0.090 / 0.063 ms
+      if (oversub < 1) oversub = 1;
+    }
+    int chunks = (ctx->num_sms * oversub + ni - 1) / ni;
     const int max_chunks = (a->hw + vy - 1) / vy;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
@@ -537,6 +772,31 @@ extern "C" int mdk_groupnorm_f16(mdk_ctx* ctx, const mdk_gn_args* a, void* strea
     q.nchunks = chunks;
     dim3 block(vx, vy);
     dim3 grid(chunks, ni);
+    int bulk = -1;   // read per call: tests switch kernels in-process
+    {
+      const char* e = getenv("MDK_GN_BULK");
+      bulk = e ? atoi(e) : 0;   // measured: no gain over the register-staged kernels (0.149 vs 0.145 ms at L0): off
+    }
+    // bulk (cp.async.bulk ring) kernels: sources 16-byte aligned, one pixel of both sources fits a stage
+    q.stage_pix = GN_STAGE_BYTES / (C * 2);
+    const bool can_bulk = bulk && q.stage_pix >= 1 && (reinterpret_cast<uintptr_t>(q.x0) & 15) == 0 &&
+                          (q.x1 == nullptr || (reinterpret_cast<uintptr_t>(q.x1) & 15) == 0);
+    if (can_bulk) {
+      const size_t ring = static_cast<size_t>(GN_STAGES) * GN_STAGE_BYTES;
+      const size_t smem_s = ring + stats_smem;
+      const size_t smem_a = ring + static_cast<size_t>(GN_MAX_CHUNKS) * 64 * 2 * sizeof(float);
+      static unsigned long long gn_attr_mask = 0;
+      if (((gn_attr_mask >> (ctx->device & 63)) & 1ull) == 0) {
+        MDK_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+        MDK_CHECK_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+        gn_attr_mask |= 1ull << (ctx->device & 63);
+      }
+      MDK_CHECK_CUDA(launch_pdl(gn_stats_bulk_kernel, grid, block, smem_s, stream, q));
+      count_launch();
+      MDK_CHECK_CUDA(launch_pdl(gn_apply_bulk_kernel, grid, block, smem_a, stream, q));
+      count_launch();
+      continue;
+    }
     MDK_CHECK_CUDA(launch_pdl(gn_stats_kernel, grid, block, stats_smem, stream, q));
     count_launch();
     MDK_CHECK_CUDA(launch_pdl(gn_apply_kernel, grid, block, 0, stream, q));

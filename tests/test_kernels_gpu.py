@@ -45,6 +45,12 @@ def test_groupnorm_layernorm():
     assert D.check_norms()
 
 
+def test_groupnorm_bulk_copy_kernels(monkeypatch):
+    """The cp.async.bulk-staged GroupNorm kernels (time-neutral, off by default) stay parity-green."""
+    monkeypatch.setenv("MDK_GN_BULK", "1")
+    assert D.check_norms()
+
+
 def test_temporal_attention_incl_sharded_layout():
     assert D.check_temporal()
 
