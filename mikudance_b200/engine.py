@@ -70,7 +70,7 @@ class UNetEngine:
                                ".to(dtype=torch.float16) like scripts/inference_video.py does")
         self._setup(model, p.device)
 
-    def _setup(self, model, dev):
+    def _setup(self, model, dev, packed_file=None):
         self.model = model
         self.dev = dev
         self.cfg = model._plan_cfg
@@ -89,7 +89,22 @@ class UNetEngine:
         self.force_simt = False   # tests: run the gathered-layout temporal kernel on one GPU
         self.world = 1
         self.rank = 0
-        self._pack()
+        if packed_file is not None:      # UNet3DConditionModel.from_packed: the module holds no weights
+            from . import weight_cache
+            if not weight_cache.read_file(self, packed_file):
+                raise RuntimeError(f"{packed_file}: packed for another kernel layout / GEGLU panel width; "
+                                   "re-create it with save_packed() from the original checkpoints")
+            return
+        from .weight_cache import PackedWeightCache
+        cache = PackedWeightCache.from_env()        # MDK_WEIGHT_CACHE=<dir>
+        key = cache.load(self) if cache is not None else None
+        self.weight_cache = cache.last if cache is not None else None
+        if self.weight_cache != "hit":
+            before = set(vars(self))
+            self._pack()
+            self._packed_attrs = sorted(set(vars(self)) - before)
+            if cache is not None:
+                cache.store(self, key)
 
     # ------------------------------------------------------------------------------------------
     # weight packing

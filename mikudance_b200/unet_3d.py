@@ -230,6 +230,7 @@ class UNet3DConditionModel(nn.Module):
                  unet_use_cross_frame_attention=None, unet_use_temporal_attention=None, mode=None,
                  task_type="action", **unused):
         super().__init__()
+        self._packed_device = None     # set by from_packed(): weights exist in the engine's layout only
         mmk = dict(_DEFAULT_MM_KW)
         mmk.update(dict(motion_module_kwargs or {}))
         cfg = dict(sample_size=sample_size, in_channels=in_channels, out_channels=out_channels,
@@ -347,19 +348,66 @@ class UNet3DConditionModel(nn.Module):
 
     @property
     def dtype(self):
-        return self.conv_in.weight.dtype
+        return torch.float16 if self._packed_device is not None else self.conv_in.weight.dtype
 
     @property
     def device(self):
-        return self.conv_in.weight.device
+        return self._packed_device if self._packed_device is not None else self.conv_in.weight.device
+
+    def _packed_only(self, what):
+        if self._packed_device is not None:
+            raise RuntimeError(f"UNet3DConditionModel.{what}: this model was built by from_packed(); its weights exist "
+                               "only in the kernels' packed layout on " + str(self._packed_device) + ". Load the "
+                               "original checkpoints (from_pretrained_2d + load_state_dict) to convert or move them")
 
     def _apply(self, fn, *a, **k):
+        self._packed_only("to() / _apply")
         self._engine = None   # packed weights follow the parameters
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict=True, **k):
+        self._packed_only("load_state_dict")
         self._engine = None
         return super().load_state_dict(state_dict, strict=strict, **k)
+
+    def state_dict(self, *a, **k):
+        self._packed_only("state_dict")
+        return super().state_dict(*a, **k)
+
+    # -------------------------------------------------------------------------------------------
+    # packed checkpoint (mikudance_b200/weight_cache.py)
+    # -------------------------------------------------------------------------------------------
+    def save_packed(self, path):
+        """Write the engine's packed fp16 weights + this model's constructor kwargs to one safetensors file."""
+        from . import weight_cache
+        eng = self.engine()
+        ctor = {k: (list(v) if isinstance(v, tuple) else v) for k, v in vars(self.config).items()}
+        weight_cache.write_file(eng, str(path), weight_cache.weights_key(self, weight_cache.layout_tag(eng)), ctor=ctor)
+
+    @classmethod
+    def from_packed(cls, path, device="cuda"):
+        """A model whose module tree lives on the `meta` device (no parameter storage) and whose engine is filled
+        straight from a `save_packed` file: replaces from_pretrained_2d + load_state_dict(denoising_unet.pth) +
+        .to(fp16, cuda) (scripts/inference_video.py:101-114) with one read and one host->device copy."""
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("UNet3DConditionModel.from_packed: device must be a CUDA (sm_100a) device; "
+                               "mikudance_b200 has no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        return cls._from_packed(path, dev)
+
+    @classmethod
+    def _from_packed(cls, path, dev):
+        from . import weight_cache
+        from .engine import UNetEngine
+        with torch.device("meta"):
+            model = cls(**weight_cache.read_ctor(str(path)))
+        model._packed_device = dev
+        eng = UNetEngine.__new__(UNetEngine)
+        eng._setup(model, dev, packed_file=str(path))
+        model._engine = eng
+        return model
 
     def engine(self):
         from .engine import UNetEngine

@@ -1053,7 +1053,61 @@ def trace_attn_2s():
     return True
 
 
+def time_weight_cache():
+    """SD-1.5-sized UNet3D: start-up cost of (a) the reference's route as this repository implements it (fp32 state dict on
+    the host -> load_state_dict -> .to(fp16, cuda) -> UNetEngine._pack on the GPU), (b) pack only, (c) a MDK_WEIGHT_CACHE
+    hit (content hash + one safetensors read), (d) from_packed() (meta-device module + one read)."""
+    import tempfile
+    from mikudance_b200 import synth
+    from mikudance_b200.unet_3d import UNet3DConditionModel
+    cfg = synth.SD15_CONFIG
+    t0 = time.time()
+    m, sd = build_model(cfg)
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    t0 = time.time()
+    eng = m.engine()
+    torch.cuda.synchronize()
+    t_pack = time.time() - t0
+    x, ctx = synth.synthetic_inputs(cfg, 2, 2, 32, 32, lctx=257)
+    x, ctx = x.to(DEV, F16), ctx.to(DEV, F16)
+    y0 = m(x, torch.tensor(499), encoder_hidden_states=ctx, return_dict=False)[0]
+    with tempfile.TemporaryDirectory() as d:
+        os.environ["MDK_WEIGHT_CACHE"] = d
+        m._engine = None
+        t0 = time.time()
+        assert m.engine().weight_cache == "miss"
+        torch.cuda.synchronize()
+        t_miss = time.time() - t0
+        size = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d))
+        m._engine = None
+        t0 = time.time()
+        assert m.engine().weight_cache == "hit"
+        torch.cuda.synchronize()
+        t_hit = time.time() - t0
+        y1 = m(x, torch.tensor(499), encoder_hidden_states=ctx, return_dict=False)[0]
+        del os.environ["MDK_WEIGHT_CACHE"]
+        path = os.path.join(d, "unet.packed.safetensors")
+        t0 = time.time()
+        m.save_packed(path)
+        t_save = time.time() - t0
+        del m
+        torch.cuda.empty_cache()
+        t0 = time.time()
+        p = UNet3DConditionModel.from_packed(path, device="cuda")
+        torch.cuda.synchronize()
+        t_packed = time.time() - t0
+        y2 = p(x, torch.tensor(499), encoder_hidden_states=ctx, return_dict=False)[0]
+    ok = torch.equal(y0, y1) and torch.equal(y0, y2)
+    print(f"weight cache (SD-1.5 UNet3D, {size / 2**30:.2f} GiB packed): build module + synthetic state dict + load + to(cuda,fp16) "
+          f"{t_build:.2f} s | _pack on the GPU {t_pack:.3f} s | cache miss (hash + pack + write) {t_miss:.2f} s | cache hit (hash + read) "
+          f"{t_hit:.2f} s | save_packed {t_save:.2f} s | from_packed (meta module + read) {t_packed:.2f} s | outputs bit-identical {ok}",
+          flush=True)
+    return ok
+
+
 CHECKS = {
+    "time_weight_cache": time_weight_cache,
     "perf_vae_clip": perf_vae_clip, "vae": check_vae, "vae_sd": check_vae_sd, "clip": check_clip, "clip_vitl14": check_clip_vitl14, "trace_attn": trace_attn, "trace_attn_2s": trace_attn_2s, "ab_attn_switches": ab_attn_switches, "ab_attn_stale": ab_attn_stale, "perf_refunet": perf_refunet,
     "refunet_ops": check_refunet_ops, "refunet_tiny": check_refunet_tiny, "refunet_a": check_refunet_a,
     "unet_tiny": check_unet_tiny, "unet_a": check_unet_a,

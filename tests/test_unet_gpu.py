@@ -142,3 +142,28 @@ def test_denoise_loop_windows_graph_vs_oracle():
                             context_frames=4, context_stride=1, context_overlap=2,
                             scheduler=DDIMOracle(**kw))
     assert _rel(results[0], want) <= 5e-3, _rel(results[0], want)
+
+
+def test_packed_checkpoint_and_weight_cache_on_device(tmp_path, monkeypatch):
+    """from_packed() (meta-device module + engine filled from one file) and a MDK_WEIGHT_CACHE
+    hit run the same kernels on the same packed tensors: outputs are bit-identical to the freshly packed model."""
+    from mikudance_b200 import synth
+    from mikudance_b200.unet_3d import UNet3DConditionModel
+    cfg = synth.TINY_CONFIG
+    m, sd = D.build_model(cfg)
+    x, ctx = synth.synthetic_inputs(cfg, 2, 3, 16, 16, lctx=9)
+    x, ctx = x.to(D.DEV, D.F16), ctx.to(D.DEV, D.F16)
+    y0 = m(x, torch.tensor(499), encoder_hidden_states=ctx, return_dict=False)[0]
+    path = tmp_path / "unet.packed.safetensors"
+    m.save_packed(path)
+    p = UNet3DConditionModel.from_packed(path, device="cuda")
+    assert all(q.device.type == "meta" for q in p.parameters()) and p.device.type == "cuda" and p.dtype == D.F16
+    y1 = p(x, torch.tensor(499), encoder_hidden_states=ctx, return_dict=False)[0]
+    assert torch.equal(y0, y1)
+    monkeypatch.setenv("MDK_WEIGHT_CACHE", str(tmp_path / "cache"))
+    m2, _ = D.build_model(cfg)
+    assert m2.engine().weight_cache == "miss"
+    m3, _ = D.build_model(cfg)
+    assert m3.engine().weight_cache == "hit"
+    y3 = m3(x, torch.tensor(499), encoder_hidden_states=ctx, return_dict=False)[0]
+    assert torch.equal(y0, y3)
