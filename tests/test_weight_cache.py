@@ -147,3 +147,43 @@ def test_packed_checkpoint_roundtrip_forward_bit_exact(monkeypatch, tmp_path):
             blk.bank = [banks[name]]
         outs.append(m._engine.forward_api(x.half(), 499, ctx.half()))
     assert torch.equal(outs[0], outs[1])
+
+
+def _rank_worker(rank, world, port, cache_dir, q):
+    import sys
+    import torch.distributed as dist
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), MDK_WEIGHT_CACHE=cache_dir)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mikudance_b200 import ops, synth
+        from mikudance_b200.engine import UNetEngine
+        model = _unet3d(synth.TINY_CONFIG)
+        dist.barrier()                                   # both ranks reach the cache at the same time
+        eng = K.engine_on_cpu(UNetEngine, model)
+        dist.barrier()
+        again = K.engine_on_cpu(UNetEngine, model)
+        q.put((rank, eng.weight_cache, again.weight_cache, float(again.temb_w.double().sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ranks_sharing_one_cache_directory_gloo(tmp_path):
+    """One process per GPU: every rank may miss and write the same entry concurrently (temp file + atomic rename);
+    afterwards there is exactly one file and every rank hits it."""
+    import torch.multiprocessing as mp
+    world, port = 2, 29500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[2] for r in res] == ["hit", "hit"] and all(r[1] in ("miss", "hit") for r in res)
+    assert res[0][3] == res[1][3]
+    files = os.listdir(tmp_path)
+    assert len(files) == 1 and files[0].startswith("mdk-packed-") and ".tmp." not in files[0]
