@@ -170,3 +170,24 @@ def test_inference_script_import_surface(monkeypatch):
             d.AutoencoderKLTemporalDecoder.from_pretrained("x")
     finally:
         sys.modules.pop("diffusers", None)
+
+
+def test_integration_md_binding_stub_matches_the_header_structs():
+    """INTEGRATION.md's ctypes stub (what a reference maintainer would paste) declares mdk_gemm_args field for field as
+    mikudance_b200/_lib.py does (which test_ctypes_structs_match_the_c_header ties to include/mdk.h), and only calls
+    entry points the library exports."""
+    import ctypes as C
+    import re
+    from mikudance_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(.*?)```", text, re.S).group(1)
+    cls_src = re.search(r"(class GemmArgs\(C\.Structure\):.*?\n)\n", code, re.S).group(1)
+    ns = {"C": C}
+    exec(cls_src, ns)                                                      # the struct declaration only
+    mine = [(n, t) for n, t in ns["GemmArgs"]._fields_]
+    ref = [(n, t) for n, t in _lib.GemmArgs._fields_]
+    assert [n for n, _ in mine] == [n for n, _ in ref]
+    assert all(C.sizeof(a) == C.sizeof(b) for (_, a), (_, b) in zip(mine, ref))
+    assert C.sizeof(ns["GemmArgs"]) == C.sizeof(_lib.GemmArgs)
+    for sym in set(re.findall(r"lib\.(mdk_\w+)", code)):
+        assert sym in _lib.EXPORTS, sym
