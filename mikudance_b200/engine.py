@@ -4,8 +4,10 @@ end to end: fp16 tokens [(b f) * h * w, C] ("NHWC"); the reference's `b c f h w 
 permute copies around every conv / norm (src/models/resnet.py:13-15,24-26) do not exist here.
 
 Frame sharding: with a process group, each rank runs the UNet on its slice of the
-window's frames (both CFG branches); the only exchange is an NCCL all-gather of the temporal
-attention's K/V inside each motion module (torch.distributed plumbing, capturable in CUDA graphs).
+window's frames (one CFG branch per half of the ranks, or both on every rank); the only exchange is inside each
+motion module: a frames<->pixels all-to-all before and after the temporal transformer (default; `_motion_a2a`,
+no layout copies) or, alternatively, an NCCL all-gather of the temporal attention's K/V (`MDK_SHARD_MODE=allgather`).
+torch.distributed is the plumbing; both are capturable in CUDA graphs.
 """
 from __future__ import annotations
 
